@@ -1,0 +1,182 @@
+/*
+ * sdr_oracle.h -- CPU ORACLE (TEST INFRASTRUCTURE ONLY, never shipped, never on the product path).
+ *
+ * A statement-level C restatement of the arithmetic of sdrtrunk's (smyers119/sdrtrunk, Java) DSP hot
+ * path: polyphase channelizer -> per-channel decimation/FIR -> FM discriminator / DQPSK symbol timing
+ * recovery.  Every function cites the reference file:line it follows ("J/" =
+ * src/main/java/io/github/dsheirer/).  Same float/double types and operation order as the Java; fmaf
+ * only where Java calls Math.fma; compiled with -O2 -ffp-contract=off and no fast-math.
+ *
+ * PARITY UNPINNED: the reference ships no golden vectors / known-answer tests for this path
+ *  and no JVM exists in the build container, so fidelity to the Java is by
+ * inspection only.  Third-party arithmetic is replaced as follows: JTransforms FloatFFT_1D ->
+ * orc_ifft_* (own float32 mixed-radix FFT + a float64 direct DFT to check it); commons-math3 FastMath
+ * sin/cos/atan/sqrt -> glibc libm in double, rounded to float where the Java casts.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may use
+ * this library, and only as the checker / baseline.
+ */
+#ifndef SDR_ORACLE_H
+#define SDR_ORACLE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---------------------------------------------------------------- filter design (a1, a9) */
+enum { ORC_WIN_HAMMING = 0, ORC_WIN_BLACKMAN = 1 };
+
+int orc_window(int type, int length, double *out);
+int orc_kaiser(int length, double attenuation, double *out);
+int orc_kaiser_sinc(int length, double cutoff, double attenuation, float *out);
+double orc_evaluate(const float *filter, int length, double frequency);
+/* returns number of taps written (channels * actual taps-per-channel) or <0 on design failure */
+int orc_sinc_m2_channelizer(double channel_bandwidth, int channels, int taps_per_channel, float *out,
+                            int out_capacity);
+int orc_sinc_m2_synthesizer(double channel_sample_rate, double channel_bandwidth, int channels,
+                            int taps_per_channel, float *out);
+int orc_half_band(int length, int window_type, float *out);
+
+/* ---------------------------------------------------------------- inverse FFT (a4) */
+typedef struct orc_fft orc_fft;
+orc_fft *orc_fft_create(int n);
+void orc_fft_destroy(orc_fft *f);
+/* in place, interleaved complex float32, e^{+j...}, scaled by 1/n (JTransforms complexInverse(a,true)) */
+void orc_ifft_f32(orc_fft *f, float *a);
+/* direct O(n^2) DFT in float64 rounded to float32: the arithmetic-independent check */
+void orc_idft_f64(int n, const float *in, float *out);
+
+/* ---------------------------------------------------------------- channelizer (a2, a3, a4) */
+typedef struct orc_channelizer orc_channelizer;
+orc_channelizer *orc_chan_create(const float *taps, int n_taps, int channel_count);
+void orc_chan_destroy(orc_channelizer *c);
+/* feed n_floats interleaved I/Q; appends whole blocks (each 2*M floats, IFFT applied) to out; returns
+ * number of blocks produced.  out must hold (pending + n_floats)/M blocks. use_f64_dft selects the
+ * direct DFT instead of the float32 FFT. */
+int orc_chan_receive(orc_channelizer *c, const float *samples, int n_floats, float *out, int use_f64_dft);
+/* filter-bank stage only (no IFFT): the accumulators after the top/middle permutation */
+int orc_chan_receive_raw(orc_channelizer *c, const float *samples, int n_floats, float *out);
+
+/* ---------------------------------------------------------------- channel calculator (a5) */
+typedef struct {
+    double sample_rate;
+    int channel_count;
+    double center_frequency;
+    double oversampling;
+} orc_calc;
+/* returns count (1..), or <0: -1 out of range, -2 wrap-around, -3 internal */
+int orc_calc_channel_indexes(const orc_calc *c, long long frequency, int bandwidth, int *indexes, int cap);
+long long orc_calc_center_frequency_for_indexes(const orc_calc *c, const int *indexes, int n);
+
+/* ---------------------------------------------------------------- output processors (a6, a7, a8) */
+typedef struct {
+    float angle_i, angle_q; /* per-sample rotation */
+    float cur_i, cur_q;
+} orc_oscillator;
+void orc_osc_init(orc_oscillator *o, double frequency, double sample_rate);
+void orc_osc_set_frequency(orc_oscillator *o, double frequency, double sample_rate);
+void orc_osc_mix(orc_oscillator *o, float *samples, int n_floats);
+
+/* gather bin `bin` from n_blocks result arrays of 2*M floats each into out[2*n_blocks] */
+void orc_get_channel(const float *results, int n_blocks, int m, int bin, float *out);
+void orc_apply_gain(float *samples, int n_floats, double gain);
+
+typedef struct orc_one_channel orc_one_channel;
+orc_one_channel *orc_one_channel_create(double sample_rate, int bin, double gain);
+void orc_one_channel_destroy(orc_one_channel *p);
+void orc_one_channel_set_frequency_offset(orc_one_channel *p, long long offset);
+void orc_one_channel_process(orc_one_channel *p, const float *results, int n_blocks, int m, float *out);
+
+typedef struct orc_two_channel orc_two_channel;
+orc_two_channel *orc_two_channel_create(double sample_rate, int bin1, int bin2, const float *filter,
+                                        int filter_len, double gain);
+void orc_two_channel_destroy(orc_two_channel *p);
+void orc_two_channel_set_frequency_offset(orc_two_channel *p, long long offset);
+void orc_two_channel_process(orc_two_channel *p, const float *results, int n_blocks, int m, float *out);
+
+/* ---------------------------------------------------------------- decimation (a9, a10) */
+typedef struct orc_halfband orc_halfband;
+orc_halfband *orc_halfband_create(const float *coefficients, int length);
+void orc_halfband_destroy(orc_halfband *h);
+/* complex: n_floats multiple of 4, out n_floats/2; real: multiple of 2. returns out floats or <0 */
+int orc_halfband_decimate_complex(orc_halfband *h, const float *samples, int n_floats, float *out);
+int orc_halfband_decimate_real(orc_halfband *h, const float *samples, int n_floats, float *out);
+
+typedef struct orc_decimator orc_decimator;
+orc_decimator *orc_decimator_create(int rate); /* 0,2,4,...,1024; NULL if unsupported */
+void orc_decimator_destroy(orc_decimator *d);
+int orc_decimator_complex(orc_decimator *d, const float *samples, int n_floats, float *out);
+int orc_decimator_real(orc_decimator *d, const float *samples, int n_floats, float *out);
+
+/* ---------------------------------------------------------------- FIR (a11) */
+typedef struct orc_fir orc_fir;
+orc_fir *orc_fir_create(const float *taps, int n, float gain);
+void orc_fir_destroy(orc_fir *f);
+float orc_fir_filter(orc_fir *f, float sample);
+void orc_fir_filter_real(orc_fir *f, const float *in, int n, float *out);
+typedef struct {
+    orc_fir *i, *q;
+} orc_cfir;
+orc_cfir *orc_cfir_create(const float *taps, int n, float gain);
+void orc_cfir_destroy(orc_cfir *f);
+void orc_cfir_filter(orc_cfir *f, const float *in, int n_floats, float *out);
+
+/* ---------------------------------------------------------------- FM (a12) */
+typedef struct {
+    float prev_i, prev_q, gain;
+} orc_fm;
+void orc_fm_init(orc_fm *f, float gain);
+float orc_fm_demodulate(orc_fm *f, float i, float q);
+void orc_fm_demodulate_buffer(orc_fm *f, const float *iq, int n_floats, float *out);
+
+typedef struct {
+    double alpha, one_minus_alpha, output; /* SinglePoleIirFilter */
+    double power, threshold;
+    int state, ramp_threshold, ramp_count;
+    int squelch_changed;
+} orc_squelch;
+void orc_squelch_init(orc_squelch *s, double alpha, double threshold_db, int ramp);
+void orc_squelch_process(orc_squelch *s, double inphase, double quadrature);
+typedef struct {
+    orc_fm fm;
+    orc_squelch sq;
+    int squelch_changed;
+} orc_sqfm;
+void orc_sqfm_init(orc_sqfm *s, double alpha, double threshold_db, int ramp);
+void orc_sqfm_demodulate_buffer(orc_sqfm *s, const float *iq, int n_floats, float *out);
+
+/* ---------------------------------------------------------------- AGC (a13) */
+void orc_agc_block(const float *in, int n_floats, float *out);
+
+/* ---------------------------------------------------------------- PSK (a14-a17) */
+enum { ORC_PSK_DECISION_DIRECTED = 0, ORC_PSK_GARDNER = 1 };
+typedef struct orc_psk orc_psk;
+orc_psk *orc_psk_create(int kind, double sample_rate, double symbol_rate, double pll_bandwidth,
+                        float sample_counter_gain);
+void orc_psk_destroy(orc_psk *p);
+/* feeds n_floats interleaved I/Q; writes one byte per symbol (Dibit.getValue 0..3); returns symbol count.
+ * taps (optional, may be NULL): per symbol 4 floats {soft_i, soft_q, detected_sps, pll_frequency} */
+int orc_psk_receive(orc_psk *p, const float *iq, int n_floats, uint8_t *dibits, float *taps);
+void orc_psk_correct_inversion(orc_psk *p, double correction);
+void orc_psk_reset_pll(orc_psk *p);
+void orc_psk_get_state(const orc_psk *p, double *phase, double *freq, float *sampling_point, float *detected_sps);
+
+/* 4 dibits per byte, MSB first (DibitToByteBufferAssembler.java:58-93); returns whole bytes written */
+int orc_pack_dibits(const uint8_t *dibits, int n, uint8_t *out);
+
+/* ---------------------------------------------------------------- whole chains (a18) used as CPU baseline */
+typedef struct orc_p25_chain orc_p25_chain;
+/* kind: 0 = C4FM (FIR + AGC + DD, BW300, gain .3, 4800), 1 = LSM (no FIR, AGC, Gardner BW200 .3, 4800),
+ *       2 = HDQPSK (FIR + AGC + Gardner BW300 .1, 6000) */
+orc_p25_chain *orc_p25_chain_create(int kind, double sample_rate, const float *fir_taps, int n_taps);
+void orc_p25_chain_destroy(orc_p25_chain *c);
+/* consumes whole 1024-complex-sample buffers only (the assembler framing); n_floats multiple of 2048 */
+int orc_p25_chain_receive(orc_p25_chain *c, const float *iq, int n_floats, uint8_t *dibits, float *agc_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
