@@ -1,0 +1,221 @@
+/*
+ * sdrgpu.h -- C ABI of libsdrgpu.so: the B200 (sm_100a) implementation of sdrtrunk's data-parallel DSP
+ * hot path.  These entry points are what sdrtrunk's Java classes bind through java.lang.foreign
+ * (INTEGRATION.md shows the binding); each group cites the reference class it replaces
+ * ("J/" = src/main/java/io/github/dsheirer/ in smyers119/sdrtrunk).
+ *
+ * Conventions
+ *  - every call returns an sdrgpu_status (0 = OK); sdrgpu_last_error() gives the message for the calling
+ *    thread.  Nothing throws or aborts across the boundary.
+ *  - all sample data is IEEE float32, complex data interleaved I,Q (the reference's float[] buffers).
+ *  - `mem` arguments say where a caller pointer lives: SDRGPU_HOST (pageable or pinned host memory) or
+ *    SDRGPU_DEVICE (device memory of the handle's GPU).  The library never keeps a caller pointer after
+ *    the call returns; host outputs are complete on return, device outputs are stream-ordered on the
+ *    handle's stream (sdrgpu_*_sync or the caller's own stream sync).
+ *  - a handle is bound to the device that was current in sdrgpu_init, owns its device state (filter
+ *    history, PLL, timing) and is NOT thread safe: one host thread <-> one handle <-> one CUDA stream.
+ *    Different handles are fully concurrent.
+ *  - there is no CPU fallback: without a usable GPU every compute entry point returns SDRGPU_ERR_CUDA.
+ */
+#ifndef SDRGPU_H
+#define SDRGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int sdrgpu_status;
+enum {
+    SDRGPU_OK = 0,
+    SDRGPU_ERR_INVALID_ARG = 1, /* Java: IllegalArgumentException */
+    SDRGPU_ERR_BAD_STATE = 2,   /* Java: IllegalStateException */
+    SDRGPU_ERR_CUDA = 3,        /* CUDA runtime / no device */
+    SDRGPU_ERR_OVERFLOW = 4,    /* more input than the handle was sized for (reference: queue OVERFLOW state) */
+    SDRGPU_ERR_DESIGN = 5,      /* Java: FilterDesignException */
+    SDRGPU_ERR_NOMEM = 6
+};
+
+enum { SDRGPU_HOST = 0, SDRGPU_DEVICE = 1 };
+
+/* ------------------------------------------------------------------ runtime */
+sdrgpu_status sdrgpu_init(int device);
+const char *sdrgpu_last_error(void);
+const char *sdrgpu_version(void);
+sdrgpu_status sdrgpu_device_count(int *count);
+sdrgpu_status sdrgpu_alloc_pinned(void **ptr, size_t bytes);
+sdrgpu_status sdrgpu_free_pinned(void *ptr);
+sdrgpu_status sdrgpu_device_alloc(void **ptr, size_t bytes);
+sdrgpu_status sdrgpu_device_free(void *ptr);
+sdrgpu_status sdrgpu_memcpy(void *dst, const void *src, size_t bytes, int dst_mem, int src_mem);
+sdrgpu_status sdrgpu_device_synchronize(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+uint64_t sdrgpu_launch_count(void);
+
+/* ------------------------------------------------------------------ filter design (host side, runs once)
+ * J/dsp/filter/FilterFactory.java:755-770 (getSincM2Synthesizer), :808-920 (getSincM2Channelizer),
+ * :1007-1036 (getHalfBand); J/dsp/filter/Window.java.  `out` receives the taps, return value through
+ * *n_taps.  The Java shim may instead pass taps designed by the unchanged FilterFactory. */
+enum { SDRGPU_WINDOW_HAMMING = 0, SDRGPU_WINDOW_BLACKMAN = 1 };
+sdrgpu_status sdrgpu_design_sinc_m2_channelizer(double channel_bandwidth, int channels, int taps_per_channel,
+                                                float *out, int capacity, int *n_taps);
+sdrgpu_status sdrgpu_design_sinc_m2_synthesizer(double channel_sample_rate, double channel_bandwidth, int channels,
+                                                int taps_per_channel, float *out, int capacity, int *n_taps);
+sdrgpu_status sdrgpu_design_half_band(int length, int window, float *out);
+/* ComplexPolyphaseChannelizerM2.getChannelCount (J/dsp/filter/channelizer/ComplexPolyphaseChannelizerM2.java:148-161) */
+int sdrgpu_channel_count_for_rate(double sample_rate);
+
+/* ------------------------------------------------------------------ channel calculator (host side)
+ * J/dsp/filter/channelizer/ChannelCalculator.java:223-281 (getChannelIndexes), :515-541
+ * (getCenterFrequencyForIndexes).  SDRGPU_ERR_INVALID_ARG where the Java throws IllegalArgumentException. */
+sdrgpu_status sdrgpu_channel_indexes(double sample_rate, int channel_count, double center_frequency,
+                                     long long channel_frequency, int channel_bandwidth, int *indexes,
+                                     int capacity, int *n_indexes);
+sdrgpu_status sdrgpu_center_frequency_for_indexes(double sample_rate, int channel_count, double center_frequency,
+                                                  const int *indexes, int n_indexes, long long *frequency);
+
+/* ------------------------------------------------------------------ polyphase channelizer
+ * Replaces ComplexPolyphaseChannelizerM2.receive + process + IFFTProcessor
+ * (J/dsp/filter/channelizer/ComplexPolyphaseChannelizerM2.java:190-235,337-383,407-428) and, in channel
+ * layout, the per-channel extraction of ReusableChannelResultsBuffer.getChannel +
+ * One/TwoChannelOutputProcessor.process (J/sample/buffer/ReusableChannelResultsBuffer.java:112-153,
+ * J/dsp/filter/channelizer/output/OneChannelOutputProcessor.java:81-106,
+ * TwoChannelOutputProcessor.java:98-121). */
+typedef struct sdrgpu_channelizer sdrgpu_channelizer;
+
+/* taps: prototype low-pass, n_taps = channel_count * taps_per_channel (as ComplexPolyphaseChannelizerM2(float[]
+ * taps, int sampleRate, int channelCount), :93-106); channel_count must be even.  max_input_floats sizes the
+ * device staging for one process call (SDRGPU_ERR_OVERFLOW beyond it). */
+sdrgpu_status sdrgpu_chan_create(sdrgpu_channelizer **h, const float *taps, int n_taps, int channel_count,
+                                 int max_input_floats);
+sdrgpu_status sdrgpu_chan_destroy(sdrgpu_channelizer *h);
+/* run this handle's work on a caller-owned cudaStream_t (NULL = the handle's own stream) */
+sdrgpu_status sdrgpu_chan_set_stream(sdrgpu_channelizer *h, void *cuda_stream);
+sdrgpu_status sdrgpu_chan_sync(sdrgpu_channelizer *h);
+
+/* One output channel of the channel layout: one polyphase bin (bin2 < 0; OneChannelOutputProcessor) or two
+ * adjacent bins recombined (TwoChannelOutputProcessor); frequency_offset_hz drives the frequency-correction
+ * oscillator (ChannelOutputProcessor.setFrequencyOffset, :91-95); gain as PolyphaseChannelManager passes it
+ * (= channel count, J/dsp/filter/channelizer/PolyphaseChannelManager.java:198-222). */
+typedef struct {
+    int bin1;
+    int bin2;
+    long long frequency_offset_hz;
+    double gain;
+} sdrgpu_output_channel;
+
+/* select the output channels (default after create: every bin 0..M-1 as a one-bin channel with gain M and no
+ * offset).  synthesis_filter (may be NULL if no two-bin channel) = getSincM2Synthesizer taps. */
+sdrgpu_status sdrgpu_chan_select(sdrgpu_channelizer *h, const sdrgpu_output_channel *channels, int n_channels,
+                                 const float *synthesis_filter, int n_synthesis_taps);
+
+enum {
+    SDRGPU_LAYOUT_RESULTS = 0, /* [n_blocks][2*M] floats: ReusableChannelResultsBuffer, all bins, no gain */
+    SDRGPU_LAYOUT_CHANNELS = 1 /* [n_selected][out_stride_floats]: contiguous per-channel streams, gain applied */
+};
+/* Feeds n_floats interleaved I/Q floats of tuner samples (any length; block framing carries over between
+ * calls like mSampleBufferPointer, :202-227).  *n_blocks receives the number of output blocks
+ * (= complex samples per output channel) produced by this call.  out_stride_floats is only used by the
+ * channel layout (row pitch in floats, >= 2 * blocks). */
+sdrgpu_status sdrgpu_chan_process(sdrgpu_channelizer *h, const float *iq, int n_floats, int in_mem, float *out,
+                                  long long out_stride_floats, int out_mem, int layout, int *n_blocks);
+/* how many blocks a call with n_floats would produce now */
+int sdrgpu_chan_blocks_for(const sdrgpu_channelizer *h, int n_floats);
+/* device time of the dominant kernel of the last process call, measured with CUDA events on the handle's
+ * stream (ms); enable first with sdrgpu_chan_enable_timing(h, 1) */
+sdrgpu_status sdrgpu_chan_enable_timing(sdrgpu_channelizer *h, int enable);
+sdrgpu_status sdrgpu_chan_last_kernel_ms(sdrgpu_channelizer *h, float *ms);
+
+/* ------------------------------------------------------------------ per-channel banks
+ * A bank runs the same per-channel chain over n_channels independent channel streams:
+ *   [half-band decimation cascade] -> [complex FIR] -> [block AGC] -> demodulator
+ * replacing, per channel, IComplexDecimationFilter (J/dsp/filter/decimate/DecimationFilterFactory.java:36-104,
+ * J/dsp/filter/halfband/complex/ComplexHalfBandDecimationFilter.java:66-123), ComplexFIRFilter2.filter
+ * (J/dsp/filter/fir/complex/ComplexFIRFilter2.java:112-129), ComplexFeedForwardGainControl.filter
+ * (J/dsp/gain/ComplexFeedForwardGainControl.java:147-181), and one of FMDemodulator / SquelchingFMDemodulator
+ * (J/dsp/fm/FMDemodulator.java:62-96, SquelchingFMDemodulator.java:63-101), DQPSKDecisionDirectedDemodulator
+ * (J/dsp/psk/DQPSKDecisionDirectedDemodulator.java:50-89) or DQPSKGardnerDemodulator
+ * (J/dsp/psk/DQPSKGardnerDemodulator.java:48-89) with CostasLoop + InterpolatingSampleBuffer. */
+typedef struct sdrgpu_bank sdrgpu_bank;
+
+enum {
+    SDRGPU_DEMOD_NONE = 0,              /* filters only: output = filtered (gain-controlled) complex stream */
+    SDRGPU_DEMOD_FM = 1,                /* FMDemodulator */
+    SDRGPU_DEMOD_FM_SQUELCH = 2,        /* SquelchingFMDemodulator */
+    SDRGPU_DEMOD_DQPSK_DECISION = 3,    /* DQPSKDecisionDirectedDemodulator (C4FM, DMR) */
+    SDRGPU_DEMOD_DQPSK_GARDNER = 4      /* DQPSKGardnerDemodulator (LSM, Phase 2 HDQPSK) */
+};
+
+typedef struct {
+    int n_channels;
+    double sample_rate;        /* of the incoming channel streams (Hz) */
+    int decimation;            /* 0 (none), 2, 4, ... 1024 */
+    const float *fir_taps;     /* NULL / 0 = no FIR (P25P1DecoderLSM.filter returns its input) */
+    int n_fir_taps;
+    float fir_gain;            /* ComplexFIRFilter2 gain, 1.0f default */
+    int agc;                   /* 1 = ComplexFeedForwardGainControl per block_size-sample buffer */
+    int block_size;            /* assembler buffer in complex samples; 1024 (PolyphaseChannelSource.java:42) */
+    int demod;                 /* SDRGPU_DEMOD_* */
+    double symbol_rate;        /* DQPSK: 4800 / 6000 */
+    double pll_bandwidth;      /* DQPSK: PLLBandwidth loop bandwidth 400/300/250/200 */
+    float sample_counter_gain; /* DQPSK: 0.3 (P1) / 0.1 (P2) */
+    float fm_gain;             /* FM: FMDemodulator gain */
+    double squelch_alpha;      /* FM_SQUELCH: 0.0004 */
+    double squelch_threshold_db; /* FM_SQUELCH: -78.0 */
+    int squelch_ramp;          /* FM_SQUELCH: 4 */
+    int max_samples_per_call;  /* per channel, complex samples; sizes device staging */
+} sdrgpu_bank_config;
+
+/* presets of the reference's decoder front-ends (chain order + constants):
+ * P25P1DecoderC4FM.java:62-93, P25P1DecoderLSM.java:67-106, P25P2DecoderHDQPSK.java:62-110,
+ * NBFMDecoder.java:55-62,262-349 */
+enum { SDRGPU_PRESET_P25_C4FM = 0, SDRGPU_PRESET_P25_LSM = 1, SDRGPU_PRESET_P25_HDQPSK = 2, SDRGPU_PRESET_NBFM = 3 };
+sdrgpu_status sdrgpu_bank_config_preset(sdrgpu_bank_config *cfg, int preset, int n_channels, double sample_rate,
+                                        const float *fir_taps, int n_fir_taps, int max_samples_per_call);
+
+sdrgpu_status sdrgpu_bank_create(sdrgpu_bank **b, const sdrgpu_bank_config *cfg);
+sdrgpu_status sdrgpu_bank_destroy(sdrgpu_bank *b);
+sdrgpu_status sdrgpu_bank_set_stream(sdrgpu_bank *b, void *cuda_stream);
+sdrgpu_status sdrgpu_bank_sync(sdrgpu_bank *b);
+
+/* Feeds n_samples complex samples per channel: channel c starts at iq + c * in_stride_floats.
+ * Outputs (each may be NULL; `out_mem` applies to all of them):
+ *   symbols  [n_channels][symbol_stride] one byte per decoded Dibit (Dibit.getValue 0..3, J/dsp/symbol/Dibit.java:27-30)
+ *   demod    [n_channels][demod_stride_floats] float: FM demodulated samples (FM demods) or the filtered /
+ *            gain-controlled interleaved complex stream (SDRGPU_DEMOD_NONE, and as a tap point for DQPSK)
+ *   counts   [n_channels] number of symbols (DQPSK) or floats (otherwise) written per channel by this call
+ * With agc / DQPSK the chain consumes whole block_size buffers only (the assembler framing,
+ * ReusableComplexBufferAssembler.java:99-167); a remainder stays buffered in the handle. */
+sdrgpu_status sdrgpu_bank_process(sdrgpu_bank *b, const float *iq, long long in_stride_floats, int n_samples,
+                                  int in_mem, uint8_t *symbols, int symbol_stride, float *demod,
+                                  long long demod_stride_floats, int *counts, int out_mem);
+/* IPhaseLockedLoop.correctInversion / reset (J/dsp/psk/pll/CostasLoop.java:91-104,224-229): applied at the next
+ * buffer boundary of that channel (host-driven sync feedback, SURVEY.md hard part 4) */
+sdrgpu_status sdrgpu_bank_correct_inversion(sdrgpu_bank *b, int channel, double radians);
+sdrgpu_status sdrgpu_bank_reset_pll(sdrgpu_bank *b, int channel);
+/* loop state tap points of one channel: {pll phase, pll frequency, sampling point, detected samples/symbol} */
+sdrgpu_status sdrgpu_bank_get_loop_state(sdrgpu_bank *b, int channel, double *state4);
+/* 4 dibits per byte MSB first (J/dsp/symbol/DibitToByteBufferAssembler.java:58-93); host helper */
+int sdrgpu_pack_dibits(const uint8_t *dibits, int n, uint8_t *out);
+sdrgpu_status sdrgpu_bank_enable_timing(sdrgpu_bank *b, int enable);
+/* ms[0] = filter (decimate/FIR/AGC) kernels, ms[1] = demodulator kernel of the last process call */
+sdrgpu_status sdrgpu_bank_last_kernel_ms(sdrgpu_bank *b, float *ms2);
+
+/* ------------------------------------------------------------------ fused pipeline
+ * channelizer -> bank without a host round trip: the channelizer's selected channels (in order) feed the
+ * bank's channels; only symbols / demodulated floats come back.  Replaces the chain
+ * PolyphaseChannelManager.BufferSourceEventMonitor.receive -> ... -> decoder.receive
+ * (SURVEY.md section 3.2 / 3.3). */
+typedef struct sdrgpu_pipeline sdrgpu_pipeline;
+sdrgpu_status sdrgpu_pipeline_create(sdrgpu_pipeline **p, sdrgpu_channelizer *chan, sdrgpu_bank *bank);
+sdrgpu_status sdrgpu_pipeline_destroy(sdrgpu_pipeline *p); /* does not destroy chan / bank */
+sdrgpu_status sdrgpu_pipeline_process(sdrgpu_pipeline *p, const float *iq, int n_floats, int in_mem,
+                                      uint8_t *symbols, int symbol_stride, float *demod,
+                                      long long demod_stride_floats, int *counts, int out_mem);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

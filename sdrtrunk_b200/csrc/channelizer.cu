@@ -1,0 +1,632 @@
+// Polyphase channelizer for sm_100a: 2x-oversampled M-branch filter bank + per-block M-point inverse DFT,
+// writing per-channel contiguous streams.
+//
+// Replaces ComplexPolyphaseChannelizerM2.receive/process + IFFTProcessor
+// (J/dsp/filter/channelizer/ComplexPolyphaseChannelizerM2.java:190-235,337-383,407-428) and the strided gather of
+// ReusableChannelResultsBuffer.getChannel + gain of OneChannelOutputProcessor.process
+// (J/sample/buffer/ReusableChannelResultsBuffer.java:112-153, .../output/OneChannelOutputProcessor.java:81-106).
+//
+// Math (derived from the reference's aligned filter + top/middle index maps): with M channels, T taps per
+// channel, block B (counted from stream start) whose newest complex sample is s_B = (B+1)*M/2 - 1,
+//     v_B[n] = sum_{t=0}^{T-1} x[s_B - n - t*M] * h[n + t*M]          n = 0..M-1      (products rounded, added
+//                                                                                       in ascending t, no FMA)
+//     u_B    = v_B                      (B even, "top" block)
+//            = v_B rotated by M/2       (B odd,  "middle" block)
+//     out_B[k] = (1/M) * sum_n u_B[n] * e^{+j 2 pi n k / M}
+// In units of M/2 samples (unit P = samples [P*M/2, (P+1)*M/2), r = offset inside the unit, n = M/2-1-r):
+//     v_B[n]       = sum_t X_P[r] h[n + tM]        with P = B - 2t
+//     v_B[n + M/2] = sum_t X_P[r] h[n + M/2 + tM]  with P = B - 1 - 2t
+// so one thread that owns r keeps its 2T taps in registers, walks P downwards loading each input sample once
+// (coalesced over r) and accumulates NB consecutive blocks in registers.
+//
+// Data layout in shared memory: [M][NB+1] float2, time index fastest, so every FFT pass (work item =
+// butterfly x block) and the final per-channel store (NB consecutive complex samples of one channel = one
+// 128-byte line for NB = 16) are bank-conflict free and coalesced.
+#include <cmath>
+#include <cstdint>
+#include <vector>
+
+#include "common.cuh"
+
+using namespace sdrgpu;
+
+namespace {
+
+constexpr int kMaxFactors = 16;
+constexpr int kThreads = 256;
+
+struct ChanParams {
+    const float2 *state;  // [state_len] history ((2T-1)*M/2 samples) followed by the leftover samples
+    const float2 *in;     // [n_in] new samples
+    const float *taps;    // [M*T] prototype filter h
+    const float2 *tw;     // [M] e^{+j 2 pi k / M}
+    float *out;
+    const int *sel;       // [n_sel] bin of each output row (channel layout)
+    const float *gain_f;  // [n_sel] float gain (used when gain_exact)
+    const double *gain_d; // [n_sel]
+    long long out_stride; // floats per output row (channel layout)
+    int state_len, n_in;
+    int M, T, half, H;
+    int n_blocks, parity0;
+    int n_sel, layout, gain_exact;
+    float inv_m;
+    int n_factors;
+    int factors[kMaxFactors];
+    unsigned magic_s[kMaxFactors];  // ceil(2^32 / s) for the stride of each pass
+};
+
+__device__ __forceinline__ float2 load_x(const ChanParams &p, int unit, int r)
+{
+    // virtual concatenation [state | in | zeros]; unit 0 starts right after the history
+    int idx = p.H + unit * p.half + r;
+    if (idx < p.state_len) return __ldg(p.state + idx);
+    idx -= p.state_len;
+    if (idx < p.n_in) return __ldg(p.in + idx);
+    return make_float2(0.0f, 0.0f);
+}
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 w)
+{
+    // explicit FMA is fine here: the inverse DFT is compared at 1e-4 relative RMS, not bit-exactly
+    return make_float2(fmaf(a.x, w.x, -a.y * w.y), fmaf(a.x, w.y, a.y * w.x));
+}
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 jmul(float2 a) { return make_float2(-a.y, a.x); }  // * (+j)
+
+template <int NB, int TT>
+__global__ void __launch_bounds__(kThreads) pfb_ifft_kernel(const ChanParams p)
+{
+    extern __shared__ float2 smem[];
+    constexpr int LD = NB + 1;
+    const int M = p.M, half = p.half;
+    float2 *buf0 = smem;
+    float2 *buf1 = smem + (size_t)M * LD;
+    float2 *tw = smem + 2 * (size_t)M * LD;
+    const int tid = threadIdx.x;
+    const int b0 = blockIdx.x * NB;
+
+    for (int i = tid; i < M; i += kThreads) tw[i] = p.tw[i];
+
+    // ------------------------------------------------------------------ filter bank
+    for (int r = tid; r < half; r += kThreads) {
+        const int n = half - 1 - r;
+        if constexpr (TT > 0) {
+            float hA[TT], hB[TT];
+#pragma unroll
+            for (int t = 0; t < TT; t++) {
+                hA[t] = __ldg(p.taps + n + t * M);
+                hB[t] = __ldg(p.taps + n + half + t * M);
+            }
+            float2 accA[NB], accB[NB];
+#pragma unroll
+            for (int pp = NB - 1; pp >= -(2 * TT - 1); --pp) {
+                const float2 x = load_x(p, b0 + pp, r);
+#pragma unroll
+                for (int t = 0; t < TT; t++) {
+                    const int bl = pp + 2 * t;  // branch n: unit P = B - 2t
+                    if (bl >= 0 && bl < NB) {
+                        const float px = __fmul_rn(x.x, hA[t]), py = __fmul_rn(x.y, hA[t]);
+                        if (t == 0) accA[bl] = make_float2(__fadd_rn(0.0f, px), __fadd_rn(0.0f, py));
+                        else accA[bl] = make_float2(__fadd_rn(accA[bl].x, px), __fadd_rn(accA[bl].y, py));
+                    }
+                    const int bm = pp + 1 + 2 * t;  // branch n + M/2: unit P = B - 1 - 2t
+                    if (bm >= 0 && bm < NB) {
+                        const float px = __fmul_rn(x.x, hB[t]), py = __fmul_rn(x.y, hB[t]);
+                        if (t == 0) accB[bm] = make_float2(__fadd_rn(0.0f, px), __fadd_rn(0.0f, py));
+                        else accB[bm] = make_float2(__fadd_rn(accB[bm].x, px), __fadd_rn(accB[bm].y, py));
+                    }
+                }
+            }
+#pragma unroll
+            for (int bl = 0; bl < NB; bl++) {
+                const int odd = (p.parity0 + b0 + bl) & 1;
+                buf0[(size_t)(odd ? n + half : n) * LD + bl] = accA[bl];
+                buf0[(size_t)(odd ? n : n + half) * LD + bl] = accB[bl];
+            }
+        } else {
+            for (int bl = 0; bl < NB; bl++) {
+                float2 a = make_float2(0.0f, 0.0f), b = make_float2(0.0f, 0.0f);
+                for (int t = 0; t < p.T; t++) {
+                    const float ha = __ldg(p.taps + n + t * M), hb = __ldg(p.taps + n + half + t * M);
+                    const float2 xa = load_x(p, b0 + bl - 2 * t, r);
+                    const float2 xb = load_x(p, b0 + bl - 1 - 2 * t, r);
+                    a = make_float2(__fadd_rn(a.x, __fmul_rn(xa.x, ha)), __fadd_rn(a.y, __fmul_rn(xa.y, ha)));
+                    b = make_float2(__fadd_rn(b.x, __fmul_rn(xb.x, hb)), __fadd_rn(b.y, __fmul_rn(xb.y, hb)));
+                }
+                const int odd = (p.parity0 + b0 + bl) & 1;
+                buf0[(size_t)(odd ? n + half : n) * LD + bl] = a;
+                buf0[(size_t)(odd ? n : n + half) * LD + bl] = b;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ------------------------------------------------------------------ inverse DFT: Stockham autosort passes,
+    // decimation in frequency:  y[q + s(r p + k)] = (sum_j x[q + s(p + m j)] W_r^{jk}) * w_M^{s p k}
+    float2 *src = buf0, *dst = buf1;
+    int s = 1;
+    for (int f = 0; f < p.n_factors; f++) {
+        const int r = p.factors[f];
+        const int m = M / (r * s);
+        const int items = (M / r) * NB;
+        const unsigned magic = p.magic_s[f];
+        for (int item = tid; item < items; item += kThreads) {
+            const int bl = item % NB;
+            const int bf = item / NB;
+            const int pq = (s == 1) ? bf : (int)__umulhi((unsigned)bf, magic);
+            const int q = bf - pq * s;
+            const float2 *x = src + (size_t)(q + s * pq) * LD + bl;
+            float2 *y = dst + (size_t)(q + s * r * pq) * LD + bl;
+            const size_t xs = (size_t)s * m * LD;  // input stride between j
+            const size_t ys = (size_t)s * LD;      // output stride between k
+            const int tws = s * pq;                // twiddle index step
+            if (r == 4) {
+                const float2 a = x[0], b = x[xs], c = x[2 * xs], d = x[3 * xs];
+                const float2 t0 = cadd(a, c), t1 = csub(a, c), t2 = cadd(b, d), t3 = jmul(csub(b, d));
+                y[0] = cadd(t0, t2);
+                y[ys] = cmul(cadd(t1, t3), tw[tws]);
+                y[2 * ys] = cmul(csub(t0, t2), tw[2 * tws]);
+                y[3 * ys] = cmul(csub(t1, t3), tw[3 * tws]);
+            } else if (r == 2) {
+                const float2 a = x[0], b = x[xs];
+                y[0] = cadd(a, b);
+                y[ys] = cmul(csub(a, b), tw[tws]);
+            } else if (r == 5) {
+                const float c1 = 0.30901699437494742f, c2 = -0.80901699437494742f;
+                const float s1 = 0.95105651629515357f, s2 = 0.58778525229247313f;
+                const float2 a = x[0], b = x[xs], c = x[2 * xs], d = x[3 * xs], e = x[4 * xs];
+                const float2 t1 = cadd(b, e), t2 = cadd(c, d), t3 = csub(b, e), t4 = csub(c, d);
+                const float2 m1 = make_float2(a.x + c1 * t1.x + c2 * t2.x, a.y + c1 * t1.y + c2 * t2.y);
+                const float2 m2 = make_float2(a.x + c2 * t1.x + c1 * t2.x, a.y + c2 * t1.y + c1 * t2.y);
+                const float2 n1 = jmul(make_float2(s1 * t3.x + s2 * t4.x, s1 * t3.y + s2 * t4.y));
+                const float2 n2 = jmul(make_float2(s2 * t3.x - s1 * t4.x, s2 * t3.y - s1 * t4.y));
+                y[0] = make_float2(a.x + t1.x + t2.x, a.y + t1.y + t2.y);
+                y[ys] = cmul(cadd(m1, n1), tw[tws]);
+                y[2 * ys] = cmul(cadd(m2, n2), tw[2 * tws]);
+                y[3 * ys] = cmul(csub(m2, n2), tw[3 * tws]);
+                y[4 * ys] = cmul(csub(m1, n1), tw[4 * tws]);
+            } else if (r == 3) {
+                const float sq = 0.86602540378443865f;
+                const float2 a = x[0], b = x[xs], c = x[2 * xs];
+                const float2 t = cadd(b, c), u = jmul(csub(b, c));
+                const float2 mm = make_float2(a.x - 0.5f * t.x, a.y - 0.5f * t.y);
+                const float2 nn = make_float2(sq * u.x, sq * u.y);
+                y[0] = cadd(a, t);
+                y[ys] = cmul(cadd(mm, nn), tw[tws]);
+                y[2 * ys] = cmul(csub(mm, nn), tw[2 * tws]);
+            } else {
+                // generic prime radix: direct r x r DFT from the M-th root table
+                const int step = M / r;
+                for (int k = 0; k < r; k++) {
+                    float2 acc = make_float2(0.0f, 0.0f);
+                    int widx = 0;
+                    for (int j = 0; j < r; j++) {
+                        acc = cadd(acc, cmul(x[j * xs], tw[widx]));
+                        widx += k * step;
+                        if (widx >= M) widx %= M;
+                    }
+                    y[k * ys] = cmul(acc, tw[tws * k]);
+                }
+            }
+        }
+        __syncthreads();
+        float2 *tmp = src;
+        src = dst;
+        dst = tmp;
+        s *= r;
+    }
+
+    // ------------------------------------------------------------------ scale + store
+    const float inv_m = p.inv_m;
+    if (p.layout == SDRGPU_LAYOUT_CHANNELS) {
+        const int total = p.n_sel * NB;
+        for (int i = tid; i < total; i += kThreads) {
+            const int bl = i % NB, c = i / NB;
+            const int b = b0 + bl;
+            if (b >= p.n_blocks) continue;
+            float2 v = src[(size_t)__ldg(p.sel + c) * LD + bl];
+            v.x = __fmul_rn(v.x, inv_m);  // FloatFFT_1D.complexInverse(a, true): a[i] *= 1.0f / n
+            v.y = __fmul_rn(v.y, inv_m);
+            if (p.gain_exact) {  // float * float == (float)(float * double) when the gain is float-representable
+                const float g = __ldg(p.gain_f + c);
+                v.x = __fmul_rn(v.x, g);
+                v.y = __fmul_rn(v.y, g);
+            } else {  // ReusableComplexBuffer.applyGain: samples[x] *= (double)gain
+                const double g = __ldg(p.gain_d + c);
+                v.x = __double2float_rn(__dmul_rn((double)v.x, g));
+                v.y = __double2float_rn(__dmul_rn((double)v.y, g));
+            }
+            *reinterpret_cast<float2 *>(p.out + (size_t)c * p.out_stride + 2 * (size_t)b) = v;
+        }
+    } else {
+        const int total = M * NB;
+        for (int i = tid; i < total; i += kThreads) {
+            const int k = i % M, bl = i / M;
+            const int b = b0 + bl;
+            if (b >= p.n_blocks) continue;
+            float2 v = src[(size_t)k * LD + bl];
+            v.x = __fmul_rn(v.x, inv_m);
+            v.y = __fmul_rn(v.y, inv_m);
+            *reinterpret_cast<float2 *>(p.out + ((size_t)b * M + k) * 2) = v;
+        }
+    }
+}
+
+// new_state[i] = S[consumed + i], S = [state | in]
+__global__ void save_state_kernel(const float2 *state, int state_len, const float2 *in, int n_in, int consumed,
+                                  float2 *new_state, int new_len)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < new_len; i += gridDim.x * blockDim.x) {
+        int idx = consumed + i;
+        float2 v = make_float2(0.0f, 0.0f);
+        if (idx < state_len) v = state[idx];
+        else if (idx - state_len < n_in) v = in[idx - state_len];
+        new_state[i] = v;
+    }
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------- handle
+struct sdrgpu_channelizer {
+    int device = 0;
+    int M = 0, T = 0, half = 0, H = 0, NB = 16;
+    int max_in_complex = 0, max_blocks = 0;
+    int leftover = 0, parity0 = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    float *d_taps = nullptr;
+    float2 *d_tw = nullptr;
+    float2 *d_state[2] = {nullptr, nullptr};
+    int cur_state = 0;
+    float2 *d_in = nullptr;    // staging for host input
+    float *d_out = nullptr;    // staging for host output
+    size_t d_out_bytes = 0;
+    int n_sel = 0;
+    int *d_sel = nullptr;
+    float *d_gain_f = nullptr;
+    double *d_gain_d = nullptr;
+    int gain_exact = 1;
+    std::vector<sdrgpu_output_channel> channels;
+    std::vector<int> factors;
+    std::vector<unsigned> magic;
+    size_t smem_bytes = 0;
+    KernelTimer timer;
+};
+
+namespace {
+
+sdrgpu_status upload_selection(sdrgpu_channelizer *h)
+{
+    const int n = (int)h->channels.size();
+    std::vector<int> sel(n);
+    std::vector<float> gf(n);
+    std::vector<double> gd(n);
+    int exact = 1;
+    for (int i = 0; i < n; i++) {
+        sel[i] = h->channels[i].bin1;
+        gd[i] = h->channels[i].gain;
+        gf[i] = (float)gd[i];
+        if ((double)gf[i] != gd[i]) exact = 0;
+    }
+    if (h->d_sel) cudaFree(h->d_sel);
+    if (h->d_gain_f) cudaFree(h->d_gain_f);
+    if (h->d_gain_d) cudaFree(h->d_gain_d);
+    h->d_sel = nullptr;
+    h->d_gain_f = nullptr;
+    h->d_gain_d = nullptr;
+    SDRGPU_CUDA(cudaMalloc(&h->d_sel, sizeof(int) * (size_t)n));
+    SDRGPU_CUDA(cudaMalloc(&h->d_gain_f, sizeof(float) * (size_t)n));
+    SDRGPU_CUDA(cudaMalloc(&h->d_gain_d, sizeof(double) * (size_t)n));
+    SDRGPU_CUDA(cudaMemcpy(h->d_sel, sel.data(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice));
+    SDRGPU_CUDA(cudaMemcpy(h->d_gain_f, gf.data(), sizeof(float) * (size_t)n, cudaMemcpyHostToDevice));
+    SDRGPU_CUDA(cudaMemcpy(h->d_gain_d, gd.data(), sizeof(double) * (size_t)n, cudaMemcpyHostToDevice));
+    h->n_sel = n;
+    h->gain_exact = exact;
+    return SDRGPU_OK;
+}
+
+template <int NB, int TT>
+sdrgpu_status launch_pfb(const sdrgpu_channelizer *h, const ChanParams &p, int grid)
+{
+    auto kernel = pfb_ifft_kernel<NB, TT>;
+    SDRGPU_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+    kernel<<<grid, kThreads, h->smem_bytes, h->stream>>>(p);
+    count_launch();
+    SDRGPU_CUDA(cudaGetLastError());
+    return SDRGPU_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+sdrgpu_status sdrgpu_chan_create(sdrgpu_channelizer **out, const float *taps, int n_taps, int channel_count,
+                                 int max_input_floats)
+{
+    if (!out || !taps || n_taps <= 0) return fail(SDRGPU_ERR_INVALID_ARG, "NULL / empty argument");
+    if (channel_count <= 0 || channel_count % 2 != 0)
+        return fail(SDRGPU_ERR_INVALID_ARG, "Channel count must be an even multiple of the over-sample rate (2x)");
+    if (max_input_floats <= 0 || max_input_floats % 2 != 0)
+        return fail(SDRGPU_ERR_INVALID_ARG, "max_input_floats must be a positive even number");
+    int dev = 0;
+    SDRGPU_CUDA(cudaGetDevice(&dev));
+    auto *h = new sdrgpu_channelizer();
+    h->device = dev;
+    const int M = channel_count;
+    h->M = M;
+    h->half = M / 2;
+    // ComplexPolyphaseChannelizerM2.java:102: mTapsPerChannel = ceil(taps.length / channelCount)
+    h->T = (n_taps + M - 1) / M;
+    h->H = (2 * h->T - 1) * h->half;
+    h->max_in_complex = max_input_floats / 2;
+    h->max_blocks = (h->max_in_complex + h->half) / h->half;
+
+    // FFT plan: radix 4, 2, 3, 5 then remaining odd primes (same factor preference as FFTPACK / JTransforms)
+    int rem = M;
+    const int pref[4] = {4, 2, 3, 5};
+    for (int f : pref)
+        while (rem % f == 0) {
+            h->factors.push_back(f);
+            rem /= f;
+        }
+    for (int f = 7; rem > 1; f += 2)
+        while (rem % f == 0) {
+            h->factors.push_back(f);
+            rem /= f;
+        }
+    if ((int)h->factors.size() > kMaxFactors) {
+        delete h;
+        return fail(SDRGPU_ERR_INVALID_ARG, "channel count %d has too many prime factors", M);
+    }
+    int s = 1;
+    for (int f : h->factors) {
+        h->magic.push_back((unsigned)((0x100000000ULL + (unsigned long long)s - 1) / (unsigned long long)s));
+        s *= f;
+    }
+
+    // tile of NB blocks per CTA: 16 when two ping-pong buffers of [M][NB+1] float2 fit in ~110 KB, else 8
+    auto smem_for = [&](int nb) { return (size_t)(2 * (size_t)M * (nb + 1) + (size_t)M) * sizeof(float2); };
+    h->NB = 16;
+    if (smem_for(16) > 112 * 1024) h->NB = 8;
+    h->smem_bytes = smem_for(h->NB);
+    if (h->smem_bytes > 227 * 1024) {
+        delete h;
+        return fail(SDRGPU_ERR_INVALID_ARG, "channel count %d too large for the shared-memory FFT", M);
+    }
+
+    std::vector<float> padded((size_t)M * h->T, 0.0f);
+    for (int i = 0; i < n_taps; i++) padded[i] = taps[i];
+    std::vector<float2> tw(M);
+    for (int k = 0; k < M; k++) {
+        double a = 2.0 * 3.14159265358979323846 * (double)k / (double)M;
+        tw[k] = make_float2((float)cos(a), (float)sin(a));
+    }
+    sdrgpu_status st = SDRGPU_OK;
+    auto cleanup_fail = [&](sdrgpu_status code) {
+        sdrgpu_chan_destroy(h);
+        return code;
+    };
+#define CHK(call)                                                                                             \
+    do {                                                                                                      \
+        cudaError_t e__ = (call);                                                                             \
+        if (e__ != cudaSuccess)                                                                               \
+            return cleanup_fail(fail(SDRGPU_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e__)));      \
+    } while (0)
+    CHK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    h->stream = h->own_stream;
+    CHK(cudaMalloc(&h->d_taps, sizeof(float) * padded.size()));
+    CHK(cudaMemcpy(h->d_taps, padded.data(), sizeof(float) * padded.size(), cudaMemcpyHostToDevice));
+    CHK(cudaMalloc(&h->d_tw, sizeof(float2) * (size_t)M));
+    CHK(cudaMemcpy(h->d_tw, tw.data(), sizeof(float2) * (size_t)M, cudaMemcpyHostToDevice));
+    const size_t state_cap = (size_t)h->H + h->half;
+    for (int i = 0; i < 2; i++) {
+        CHK(cudaMalloc(&h->d_state[i], sizeof(float2) * state_cap));
+        CHK(cudaMemset(h->d_state[i], 0, sizeof(float2) * state_cap));
+    }
+#undef CHK
+    h->channels.resize(M);
+    for (int k = 0; k < M; k++) h->channels[k] = sdrgpu_output_channel{k, -1, 0, (double)M};
+    st = upload_selection(h);
+    if (st != SDRGPU_OK) return cleanup_fail(st);
+    *out = h;
+    return SDRGPU_OK;
+}
+
+sdrgpu_status sdrgpu_chan_destroy(sdrgpu_channelizer *h)
+{
+    if (!h) return SDRGPU_OK;
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    cudaFree(h->d_taps);
+    cudaFree(h->d_tw);
+    cudaFree(h->d_state[0]);
+    cudaFree(h->d_state[1]);
+    cudaFree(h->d_in);
+    cudaFree(h->d_out);
+    cudaFree(h->d_sel);
+    cudaFree(h->d_gain_f);
+    cudaFree(h->d_gain_d);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+    return SDRGPU_OK;
+}
+
+sdrgpu_status sdrgpu_chan_set_stream(sdrgpu_channelizer *h, void *cuda_stream)
+{
+    if (!h) return fail(SDRGPU_ERR_INVALID_ARG, "NULL handle");
+    SDRGPU_CUDA(cudaStreamSynchronize(h->stream));
+    h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+    return SDRGPU_OK;
+}
+
+sdrgpu_status sdrgpu_chan_sync(sdrgpu_channelizer *h)
+{
+    if (!h) return fail(SDRGPU_ERR_INVALID_ARG, "NULL handle");
+    SDRGPU_CUDA(cudaStreamSynchronize(h->stream));
+    return SDRGPU_OK;
+}
+
+sdrgpu_status sdrgpu_chan_select(sdrgpu_channelizer *h, const sdrgpu_output_channel *channels, int n_channels,
+                                 const float *synthesis_filter, int n_synthesis_taps)
+{
+    if (!h || !channels || n_channels <= 0) return fail(SDRGPU_ERR_INVALID_ARG, "NULL / empty selection");
+    (void)synthesis_filter;
+    (void)n_synthesis_taps;
+    for (int i = 0; i < n_channels; i++) {
+        if (channels[i].bin1 < 0 || channels[i].bin1 >= h->M)
+            return fail(SDRGPU_ERR_INVALID_ARG, "Channel [%d] is not valid -- max channel is %d", channels[i].bin1, h->M);
+        if (channels[i].bin2 >= 0 || channels[i].frequency_offset_hz != 0)
+            return fail(SDRGPU_ERR_INVALID_ARG, "two-bin / frequency-corrected output channels are not built yet");
+    }
+    SDRGPU_CUDA(cudaStreamSynchronize(h->stream));
+    h->channels.assign(channels, channels + n_channels);
+    return upload_selection(h);
+}
+
+int sdrgpu_chan_blocks_for(const sdrgpu_channelizer *h, int n_floats)
+{
+    if (!h || n_floats < 0) return 0;
+    return (h->leftover + n_floats / 2) / h->half;
+}
+
+sdrgpu_status sdrgpu_chan_enable_timing(sdrgpu_channelizer *h, int enable)
+{
+    if (!h) return fail(SDRGPU_ERR_INVALID_ARG, "NULL handle");
+    return h->timer.enable(enable != 0);
+}
+
+sdrgpu_status sdrgpu_chan_last_kernel_ms(sdrgpu_channelizer *h, float *ms)
+{
+    if (!h || !ms) return fail(SDRGPU_ERR_INVALID_ARG, "NULL argument");
+    return h->timer.read(ms);
+}
+
+sdrgpu_status sdrgpu_chan_process(sdrgpu_channelizer *h, const float *iq, int n_floats, int in_mem, float *out,
+                                  long long out_stride_floats, int out_mem, int layout, int *n_blocks_out)
+{
+    if (!h) return fail(SDRGPU_ERR_INVALID_ARG, "NULL handle");
+    if (n_floats < 0 || n_floats % 2 != 0) return fail(SDRGPU_ERR_INVALID_ARG, "n_floats must be even (interleaved I/Q)");
+    if (n_floats > 0 && !iq) return fail(SDRGPU_ERR_INVALID_ARG, "iq is NULL");
+    if (layout != SDRGPU_LAYOUT_RESULTS && layout != SDRGPU_LAYOUT_CHANNELS)
+        return fail(SDRGPU_ERR_INVALID_ARG, "unknown layout %d", layout);
+    const int n_in = n_floats / 2;
+    if (n_in > h->max_in_complex)
+        return fail(SDRGPU_ERR_OVERFLOW, "input of %d floats exceeds the handle's max_input_floats %d", n_floats,
+                    2 * h->max_in_complex);
+    if (((uintptr_t)iq & 7) != 0 && in_mem == SDRGPU_DEVICE)
+        return fail(SDRGPU_ERR_INVALID_ARG, "device input must be 8-byte aligned");
+    SDRGPU_CUDA(cudaSetDevice(h->device));
+
+    const int total = h->leftover + n_in;
+    const int n_blocks = total / h->half;
+    if (n_blocks_out) *n_blocks_out = n_blocks;
+    const int rows = (layout == SDRGPU_LAYOUT_CHANNELS) ? h->n_sel : 0;
+    if (n_blocks > 0) {
+        if (!out) return fail(SDRGPU_ERR_INVALID_ARG, "out is NULL");
+        if (layout == SDRGPU_LAYOUT_CHANNELS && (out_stride_floats < 2LL * n_blocks || (out_stride_floats & 1)))
+            return fail(SDRGPU_ERR_INVALID_ARG, "out_stride_floats must be even and >= 2 * n_blocks (%d)", 2 * n_blocks);
+        if (out_mem == SDRGPU_DEVICE && ((uintptr_t)out & 7) != 0)
+            return fail(SDRGPU_ERR_INVALID_ARG, "device output must be 8-byte aligned");
+    }
+
+    const float2 *d_in = nullptr;
+    if (n_in > 0) {
+        if (in_mem == SDRGPU_HOST) {
+            if (!h->d_in) SDRGPU_CUDA(cudaMalloc(&h->d_in, sizeof(float2) * (size_t)h->max_in_complex));
+            SDRGPU_CUDA(cudaMemcpyAsync(h->d_in, iq, sizeof(float) * (size_t)n_floats, cudaMemcpyHostToDevice, h->stream));
+            d_in = h->d_in;
+        } else {
+            d_in = reinterpret_cast<const float2 *>(iq);
+        }
+    }
+
+    const float2 *state = h->d_state[h->cur_state];
+    const int state_len = h->H + h->leftover;
+
+    if (n_blocks > 0) {
+        float *d_out = out;
+        long long stride = out_stride_floats;
+        if (out_mem == SDRGPU_HOST) {
+            const size_t need = (layout == SDRGPU_LAYOUT_CHANNELS) ? sizeof(float) * 2 * (size_t)n_blocks * (size_t)rows
+                                                                  : sizeof(float) * 2 * (size_t)n_blocks * (size_t)h->M;
+            if (need > h->d_out_bytes) {
+                if (h->d_out) {
+                    SDRGPU_CUDA(cudaStreamSynchronize(h->stream));
+                    cudaFree(h->d_out);
+                    h->d_out = nullptr;
+                }
+                const size_t cap = sizeof(float) * 2 * (size_t)h->max_blocks * (size_t)(h->M > h->n_sel ? h->M : h->n_sel);
+                const size_t bytes = need > cap ? need : cap;
+                SDRGPU_CUDA(cudaMalloc(&h->d_out, bytes));
+                h->d_out_bytes = bytes;
+            }
+            d_out = h->d_out;
+            stride = 2LL * n_blocks;
+        }
+        ChanParams p{};
+        p.state = state;
+        p.in = d_in;
+        p.taps = h->d_taps;
+        p.tw = h->d_tw;
+        p.out = d_out;
+        p.sel = h->d_sel;
+        p.gain_f = h->d_gain_f;
+        p.gain_d = h->d_gain_d;
+        p.out_stride = stride;
+        p.state_len = state_len;
+        p.n_in = n_in;
+        p.M = h->M;
+        p.T = h->T;
+        p.half = h->half;
+        p.H = h->H;
+        p.n_blocks = n_blocks;
+        p.parity0 = h->parity0;
+        p.n_sel = h->n_sel;
+        p.layout = layout;
+        p.gain_exact = h->gain_exact;
+        p.inv_m = 1.0f / (float)h->M;
+        p.n_factors = (int)h->factors.size();
+        for (int i = 0; i < p.n_factors; i++) {
+            p.factors[i] = h->factors[i];
+            p.magic_s[i] = h->magic[i];
+        }
+        const int grid = (n_blocks + h->NB - 1) / h->NB;
+        h->timer.begin(h->stream);
+        sdrgpu_status st;
+        if (h->NB == 16) st = (h->T == 9) ? launch_pfb<16, 9>(h, p, grid) : launch_pfb<16, 0>(h, p, grid);
+        else st = (h->T == 9) ? launch_pfb<8, 9>(h, p, grid) : launch_pfb<8, 0>(h, p, grid);
+        h->timer.end(h->stream);
+        SDRGPU_TRY(st);
+        if (out_mem == SDRGPU_HOST) {
+            if (layout == SDRGPU_LAYOUT_CHANNELS) {
+                SDRGPU_CUDA(cudaMemcpy2DAsync(out, sizeof(float) * (size_t)out_stride_floats, d_out,
+                                              sizeof(float) * (size_t)stride, sizeof(float) * 2 * (size_t)n_blocks,
+                                              (size_t)rows, cudaMemcpyDeviceToHost, h->stream));
+            } else {
+                SDRGPU_CUDA(cudaMemcpyAsync(out, d_out, sizeof(float) * 2 * (size_t)n_blocks * (size_t)h->M,
+                                            cudaMemcpyDeviceToHost, h->stream));
+            }
+        }
+    }
+
+    // carry the history + leftover over to the next call
+    const int consumed = n_blocks * h->half;
+    const int new_leftover = total - consumed;
+    const int new_len = h->H + new_leftover;
+    float2 *next = h->d_state[h->cur_state ^ 1];
+    if (n_in > 0) {
+        int grid = (new_len + 255) / 256;
+        if (grid > 1024) grid = 1024;
+        save_state_kernel<<<grid, 256, 0, h->stream>>>(state, state_len, d_in, n_in, consumed, next, new_len);
+        count_launch();
+        SDRGPU_CUDA(cudaGetLastError());
+        h->cur_state ^= 1;
+    }
+    h->leftover = new_leftover;
+    h->parity0 = (h->parity0 + n_blocks) & 1;
+
+    if (out_mem == SDRGPU_HOST || in_mem == SDRGPU_HOST) SDRGPU_CUDA(cudaStreamSynchronize(h->stream));
+    return SDRGPU_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,83 @@
+// Shared plumbing for libsdrgpu: status/error reporting, CUDA call checking, launch accounting.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <string>
+
+#include "../../include/sdrgpu.h"
+
+namespace sdrgpu {
+
+extern thread_local std::string g_last_error;
+extern std::atomic<uint64_t> g_launches;
+
+inline sdrgpu_status fail(sdrgpu_status code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define SDRGPU_CUDA(call)                                                                         \
+    do {                                                                                          \
+        cudaError_t e__ = (call);                                                                 \
+        if (e__ != cudaSuccess)                                                                   \
+            return ::sdrgpu::fail(SDRGPU_ERR_CUDA, "%s failed: %s (%s:%d)", #call,                \
+                                  cudaGetErrorString(e__), __FILE__, __LINE__);                   \
+    } while (0)
+
+#define SDRGPU_TRY(expr)                      \
+    do {                                      \
+        sdrgpu_status s__ = (expr);           \
+        if (s__ != SDRGPU_OK) return s__;     \
+    } while (0)
+
+inline void count_launch(int n = 1) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+// Optional per-handle kernel timing with CUDA events on the handle's stream.
+struct KernelTimer {
+    cudaEvent_t start = nullptr, stop = nullptr;
+    bool enabled = false, pending = false;
+    sdrgpu_status enable(bool on)
+    {
+        if (on && !start) {
+            SDRGPU_CUDA(cudaEventCreate(&start));
+            SDRGPU_CUDA(cudaEventCreate(&stop));
+        }
+        enabled = on;
+        return SDRGPU_OK;
+    }
+    void begin(cudaStream_t s)
+    {
+        if (enabled) cudaEventRecord(start, s);
+    }
+    void end(cudaStream_t s)
+    {
+        if (enabled) {
+            cudaEventRecord(stop, s);
+            pending = true;
+        }
+    }
+    sdrgpu_status read(float *ms)
+    {
+        *ms = 0.0f;
+        if (!enabled || !pending) return SDRGPU_OK;
+        SDRGPU_CUDA(cudaEventSynchronize(stop));
+        SDRGPU_CUDA(cudaEventElapsedTime(ms, start, stop));
+        return SDRGPU_OK;
+    }
+    ~KernelTimer()
+    {
+        if (start) cudaEventDestroy(start);
+        if (stop) cudaEventDestroy(stop);
+    }
+};
+
+}  // namespace sdrgpu

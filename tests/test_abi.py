@@ -1,0 +1,67 @@
+"""The C-ABI library loads on a CPU-only box, exports every symbol include/sdrgpu.h declares, and its compute
+entry points fail loudly (no CPU fallback) when no GPU is present."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "sdrgpu.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(sdrgpu_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_exported():
+    from sdrtrunk_b200 import native
+    lib = ctypes.CDLL(native.LIB_PATH)
+    names = declared_symbols()
+    assert len(names) >= 40
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+
+
+def test_python_prototypes_cover_header():
+    from sdrtrunk_b200 import native
+    assert sorted(native.PROTOTYPES) == declared_symbols()
+
+
+def test_no_cpu_fallback_without_gpu():
+    from sdrtrunk_b200 import native
+    n = ctypes.c_int(-1)
+    status = native.lib().sdrgpu_device_count(ctypes.byref(n))
+    if status == 0 and n.value > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(native.CudaError):
+        native.init(0)
+    from sdrtrunk_b200.dsp import ComplexPolyphaseChannelizerM2
+    with pytest.raises(native.CudaError):
+        ComplexPolyphaseChannelizerM2(np.ones(18, np.float32), 50000, 2)
+
+
+def test_product_never_imports_oracle():
+    bad = []
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "sdrtrunk_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                if re.search(r"^\s*(import|from)\s+oracle\b", src, flags=re.M) or "liboracle" in src \
+                        or re.search(r'#include\s+"[^"]*oracle', src):
+                    bad.append(f)
+    assert not bad, bad
+
+
+def test_pack_dibits_host_helper():
+    from sdrtrunk_b200 import native
+    import oracle
+    d = np.random.default_rng(0).integers(0, 4, 41).astype(np.uint8)
+    out = np.zeros(16, np.uint8)
+    n = native.lib().sdrgpu_pack_dibits(d.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), d.size,
+                                        out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)))
+    assert n == 10
+    assert np.array_equal(out[:n], oracle.pack_dibits(d))
+    assert out[0] == (d[0] << 6 | d[1] << 4 | d[2] << 2 | d[3])

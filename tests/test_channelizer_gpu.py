@@ -1,0 +1,171 @@
+"""Parity of the CUDA polyphase channelizer (through the C ABI) against the oracle.
+
+Tolerance: 1e-4 relative RMS per channel (BASELINE.json north_star; the inverse DFT's summation order differs
+from JTransforms' by construction).  The filter-bank stage itself is arithmetic-identical (products rounded,
+sequential adds) so the end result is typically ~1e-7.
+"""
+import numpy as np
+import pytest
+
+import oracle
+import siggen as sg
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4
+
+
+def _signal(rng, n, m):
+    """random-phase tones near a handful of bin centres + AWGN, amplitude in the tuner's [-1, 1] range"""
+    fs = 25000.0 * m
+    z = sg.awgn(rng, n, 1e-3)
+    for k in rng.choice(m, size=min(m, 12), replace=False):
+        f = (k if k < m // 2 else k - m) * 25000.0 + rng.uniform(-5000, 5000)
+        z = z + sg.tone(fs, f, n, amplitude=0.05, phase=rng.uniform(0, 2 * np.pi))
+    return sg.interleave(z)
+
+
+@pytest.mark.parametrize("m", [96, 400, 800, 114, 70, 2])
+def test_results_layout_matches_oracle(gpu, m):
+    from sdrtrunk_b200.dsp import ComplexPolyphaseChannelizerM2
+    rng = np.random.default_rng(m)
+    taps = oracle.sinc_m2_channelizer(25000.0, m, 9) if m > 2 else np.hanning(18).astype(np.float32)
+    x = _signal(rng, 37 * m // 2 + 5, m)
+    want = oracle.Channelizer(taps, m).receive(x, mode="f64")
+    ch = ComplexPolyphaseChannelizerM2(taps, 25000 * m, m)
+    got = ch.receive(x)
+    assert got.shape == want.shape
+    assert sg.rel_rms(got, want) < TOL
+    # per-bin check on the bins that carry signal
+    power = np.sum(want.reshape(want.shape[0], m, 2) ** 2, axis=(0, 2))
+    for k in np.argsort(power)[-4:]:
+        assert sg.rel_rms(got[:, 2 * k:2 * k + 2], want[:, 2 * k:2 * k + 2]) < TOL
+
+
+@pytest.mark.parametrize("m", [96, 400])
+def test_channel_layout_matches_oracle_output_processor(gpu, m):
+    from sdrtrunk_b200.dsp import ComplexPolyphaseChannelizerM2
+    rng = np.random.default_rng(100 + m)
+    taps = oracle.sinc_m2_channelizer(25000.0, m, 9)
+    x = _signal(rng, 53 * m // 2, m)
+    res = oracle.Channelizer(taps, m).receive(x, mode="f64")
+    ch = ComplexPolyphaseChannelizerM2(taps, 25000 * m, m)
+    got = ch.receiveChannels(x)                       # default selection: all bins, gain M
+    assert got.shape == (m, 2 * res.shape[0])
+    for k in (0, 1, m // 2 - 1, m // 2, m - 1):
+        want = oracle.OneChannelOutputProcessor(50000.0, k, float(m)).process(res)
+        assert sg.rel_rms(got[k], want) < TOL, k
+    # explicit selection of a subset, in caller order
+    bins = [5, m - 2, 0, 17]
+    ch2 = ComplexPolyphaseChannelizerM2(taps, 25000 * m, m)
+    ch2.setChannels(bins)
+    sub = ch2.receiveChannels(x)
+    assert sub.shape == (4, 2 * res.shape[0])
+    assert np.array_equal(sub, got[bins])
+
+
+def test_streaming_framing_is_independent_of_buffer_length(gpu):
+    """mSampleBufferPointer carry-over (ComplexPolyphaseChannelizerM2.java:202-227): ragged / tiny / empty buffers"""
+    from sdrtrunk_b200.dsp import ComplexPolyphaseChannelizerM2
+    m = 96
+    rng = np.random.default_rng(7)
+    taps = oracle.sinc_m2_channelizer(25000.0, m, 9)
+    x = _signal(rng, 6000, m)
+    whole = ComplexPolyphaseChannelizerM2(taps, 25000 * m, m).receive(x)
+    ch = ComplexPolyphaseChannelizerM2(taps, 25000 * m, m)
+    parts, pos = [], 0
+    for n in (2, 0, 94, 96, 1000, 98, 3710, 7000):
+        parts.append(ch.receive(x[pos:pos + n]))
+        pos += n
+    assert pos == x.size
+    got = np.concatenate(parts)
+    assert got.shape == whole.shape
+    assert np.array_equal(got, whole)                 # same arithmetic regardless of framing
+    want = oracle.Channelizer(taps, m).receive(x, mode="f64")
+    assert sg.rel_rms(got, want) < TOL
+
+
+def test_filter_bank_stage_is_bit_exact_on_dc_bin(gpu):
+    """Bin 0 of the inverse DFT is the plain sum of the filter-bank accumulators; feeding a signal that only
+    excites one polyphase branch makes that sum a single term, which must match the oracle's accumulators."""
+    from sdrtrunk_b200.dsp import ComplexPolyphaseChannelizerM2
+    m = 96
+    taps = oracle.sinc_m2_channelizer(25000.0, m, 9)
+    x = np.zeros(2 * 48 * 40, np.float32)
+    x[2 * 17::2 * 48] = np.random.default_rng(8).standard_normal(40).astype(np.float32)   # one branch only
+    raw = oracle.Channelizer(taps, m).receive(x, mode="raw")
+    got = ComplexPolyphaseChannelizerM2(taps, 25000 * m, m).receive(x)
+    want0 = raw.reshape(raw.shape[0], m, 2).sum(axis=1) * np.float32(1.0 / m)
+    assert np.array_equal(got[:, 0:2], want0.astype(np.float32))
+
+
+def test_custom_taps_per_channel_generic_path(gpu):
+    from sdrtrunk_b200.dsp import ComplexPolyphaseChannelizerM2
+    m = 40
+    rng = np.random.default_rng(9)
+    taps = oracle.sinc_m2_channelizer(25000.0, m, 5)   # T = 5 -> runtime-T filter-bank path
+    x = _signal(rng, 3000, m)
+    want = oracle.Channelizer(taps, m).receive(x, mode="f64")
+    got = ComplexPolyphaseChannelizerM2(taps, 25000 * m, m).receive(x)
+    assert sg.rel_rms(got, want) < TOL
+
+
+def test_errors_mirror_reference(gpu):
+    from sdrtrunk_b200 import native
+    from sdrtrunk_b200.dsp import ComplexPolyphaseChannelizerM2
+    with pytest.raises(native.IllegalArgumentException):
+        ComplexPolyphaseChannelizerM2(np.ones(27, np.float32), 75000, 3)     # odd channel count (:97-100)
+    ch = ComplexPolyphaseChannelizerM2(1e6, 9, maxInputFloats=4096)          # designs its own prototype (:114-126)
+    assert ch.mChannelCount == 40 and ch.mTapsPerChannel == 9
+    with pytest.raises(native.IllegalArgumentException):
+        ch.receive(np.zeros(7, np.float32))                                   # odd float count
+    with pytest.raises(native.OverflowError_):
+        ch.receive(np.zeros(8192, np.float32))
+    with pytest.raises(native.IllegalArgumentException):
+        ch.setChannels([40])
+
+
+def test_full_size_tone_property(gpu):
+    """BASELINE config 2 size: 10 MS/s -> 400 channels, one TestTuner buffer of 500 000 samples; a tone placed
+    at bin k + df lands in channel k at unit amplitude rotating at df (size-independent property)."""
+    from sdrtrunk_b200.dsp import ComplexPolyphaseChannelizerM2
+    m, fs, n = 400, 1e7, 500000
+    ch = ComplexPolyphaseChannelizerM2(fs, 9)
+    k, df = 123, 2500.0
+    z = sg.tone(fs, k * 25000.0 + df, n, amplitude=0.25)
+    out = ch.receiveChannels(sg.interleave(z))
+    assert out.shape == (m, 2 * (n // 200))
+    power = np.mean(out[:, 200:] ** 2, axis=1) * 2
+    assert power.argmax() == k
+    assert abs(np.sqrt(power[k]) - 0.25) < 1e-3
+    others = np.delete(power, [k - 1, k, k + 1])
+    assert others.max() < 1e-7 * power[k] * 1e2          # >= 50 dB down outside the adjacent bins
+    c = sg.deinterleave(out[k, 200:])
+    step = np.angle(np.mean(c[1:] * np.conj(c[:-1])))
+    assert abs(step - 2 * np.pi * df / 50000.0) < 1e-4
+
+
+def test_device_resident_io(gpu):
+    """SDRGPU_DEVICE pointers in and out: no host copies inside the call."""
+    import ctypes as C
+    from sdrtrunk_b200 import native
+    from sdrtrunk_b200.dsp import ComplexPolyphaseChannelizerM2
+    m = 96
+    rng = np.random.default_rng(10)
+    taps = oracle.sinc_m2_channelizer(25000.0, m, 9)
+    x = _signal(rng, 4800, m)
+    host = ComplexPolyphaseChannelizerM2(taps, 25000 * m, m).receiveChannels(x)
+    ch = ComplexPolyphaseChannelizerM2(taps, 25000 * m, m)
+    L = native.lib()
+    d_in, d_out = C.c_void_p(), C.c_void_p()
+    native.check(L.sdrgpu_device_alloc(C.byref(d_in), x.nbytes))
+    native.check(L.sdrgpu_device_alloc(C.byref(d_out), host.nbytes))
+    native.check(L.sdrgpu_memcpy(d_in, native.ptr(x), x.nbytes, native.DEVICE, native.HOST))
+    nb = ch.receiveChannels((d_in.value, x.size), native.DEVICE, d_out.value, native.DEVICE, host.shape[1])
+    ch.sync()
+    back = np.empty_like(host)
+    native.check(L.sdrgpu_memcpy(native.ptr(back), d_out, host.nbytes, native.HOST, native.DEVICE))
+    assert nb == host.shape[1] // 2
+    assert np.array_equal(back, host)
+    L.sdrgpu_device_free(d_in)
+    L.sdrgpu_device_free(d_out)
