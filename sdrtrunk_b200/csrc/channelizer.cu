@@ -339,6 +339,8 @@ sdrgpu_status launch_pfb(const sdrgpu_channelizer *h, const ChanParams &p, int g
 
 }  // namespace
 
+int sdrgpu::chan_selected_count(const sdrgpu_channelizer *h) { return h ? h->n_sel : 0; }
+
 extern "C" {
 
 sdrgpu_status sdrgpu_chan_create(sdrgpu_channelizer **out, const float *taps, int n_taps, int channel_count,
@@ -454,8 +456,10 @@ sdrgpu_status sdrgpu_chan_destroy(sdrgpu_channelizer *h)
 sdrgpu_status sdrgpu_chan_set_stream(sdrgpu_channelizer *h, void *cuda_stream)
 {
     if (!h) return fail(SDRGPU_ERR_INVALID_ARG, "NULL handle");
+    cudaStream_t next = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+    if (next == h->stream) return SDRGPU_OK;
     SDRGPU_CUDA(cudaStreamSynchronize(h->stream));
-    h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+    h->stream = next;
     return SDRGPU_OK;
 }
 

@@ -39,6 +39,9 @@ inline sdrgpu_status fail(sdrgpu_status code, const char *fmt, ...)
         if (s__ != SDRGPU_OK) return s__;     \
     } while (0)
 
+// number of output rows the channelizer currently selects (channelizer.cu)
+int chan_selected_count(const sdrgpu_channelizer *h);
+
 inline void count_launch(int n = 1) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 
 // Optional per-handle kernel timing with CUDA events on the handle's stream.
