@@ -1,17 +1,18 @@
 #!/usr/bin/env python3
 """bench.py -- headline benchmark of the B200 DSP hot path (contract: see the task's "Measurement" section).
 
-    python bench.py --gpus N --steps K --warmup W [--workload NAME] [--impl reference]
+    python bench.py --gpus N --steps K --warmup W [--workload NAME] [--impl reference] [--no-extra]
 
-One "step" = one pass of the hot path over one batch of synthetic tuner I/Q (1 s of signal by default).
+One "step" = one pass of the hot path over one batch of synthetic tuner I/Q (1 s of a 10 MS/s stream).
 N > 1 is launched by torchrun, one rank per GPU; tuner streams are independent so every rank processes its own
 stream (weak scaling, no data-path collective); torch.distributed is used for the barrier and the
 max-over-ranks time only.
 
-Keys of the JSON line (rank 0): value = whole-job complex MS/s with inputs resident in HBM; e2e = the same
+Keys of the JSON line (rank 0): value = whole-job input complex MS/s with inputs resident in HBM; e2e = the same
 through the C ABI with pinned HOST buffers (H2D + D2H inside the timed region); roofline = dominant kernel
 against the measured HBM peak; cpu_baseline = the oracle (CPU restatement of the reference's Java path) timed
-on this box's host cores on a bounded sample.
+on this box's host cores on a bounded sample; chain_c4fm = the same measurements for BASELINE configs[2]
+(channelizer -> FIR -> AGC -> DQPSK timing recovery on all 400 channels) as a secondary result.
 """
 import argparse
 import ctypes as C
@@ -30,6 +31,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "channelized+demodulated complex MS/s and real-time channel count at 1/2/4/8 GPU"
 UNIT = "MS/s"
+FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12   # FFMA lanes x 2 flop x max SM clock
 
 WORKLOADS = {
     # BASELINE.json configs[1]: polyphase channelizer, 10 MS/s -> 400 x 25 kHz channels
@@ -54,6 +56,14 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def load_traffic(kernel):
+    """per-launch DRAM bytes of `kernel` from the committed ncu --set full summary (profiles/traffic.json)"""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(kernel)
+    except Exception:
+        return None
+
+
 # ---------------------------------------------------------------------------------------------- clocks sampler
 class ClockSampler:
     FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -68,7 +78,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
@@ -125,76 +135,97 @@ def synth_input_numpy(n_complex, m, seed):
     return out
 
 
-def cpu_baseline(workload, threads, target_seconds=6.0):
-    """Times the oracle (kind "port": CPU restatement of the reference Java path; no JVM here) on `threads` host
-    threads, one independent tuner stream per thread (the oracle releases the GIL inside ctypes calls)."""
-    import oracle
-    cfg = WORKLOADS[workload]
-    fs = cfg["fs"]
-    m = int(fs / 25000) // 2 * 2
-    taps = oracle.sinc_m2_channelizer(fs / m, m, cfg["taps_per_channel"])
-    # bounded sample: 2 M input samples, or 4 whole 1024-sample assembler buffers per channel for the demod chain
-    n_complex = 4 * 1024 * (m // 2) if cfg["demod"] else 2000000
-    x = synth_input_numpy(n_complex, m, 1)
-    fir = c4fm_fir_taps() if cfg["demod"] == "c4fm" else None
+class CpuChain:
+    """The oracle (kind "port": CPU restatement of the reference Java path; no JVM here) arranged like the
+    reference runs it: one channelizer per tuner stream, one output processor + decoder chain per channel.  One
+    independent tuner stream per host thread (the oracle releases the GIL inside its ctypes calls)."""
 
-    def make_state():
-        st = {"chan": oracle.Channelizer(taps, m)}
-        if cfg["demod"] == "c4fm":
-            st["procs"] = [oracle.OneChannelOutputProcessor(50000.0, k, float(m)) for k in range(m)]
-            st["chains"] = [oracle.P25Chain(oracle.C4FM, 50000.0, fir) for _ in range(m)]
-        return st
+    def __init__(self, workload, threads):
+        import oracle
+        self.cfg = WORKLOADS[workload]
+        self.workload = workload
+        fs = self.cfg["fs"]
+        self.m = m = int(fs / 25000) // 2 * 2
+        taps = oracle.sinc_m2_channelizer(fs / m, m, self.cfg["taps_per_channel"])
+        # bounded sample: 1 M input samples, or 2 whole 1024-sample assembler buffers per channel for the chain
+        self.n_complex = 2 * 1024 * (m // 2) if self.cfg["demod"] else 1000000
+        self.x = synth_input_numpy(self.n_complex, m, 1)
+        fir = c4fm_fir_taps() if self.cfg["demod"] == "c4fm" else None
+        self.threads = threads
+        self.states = []
+        for _ in range(threads):
+            st = {"chan": oracle.Channelizer(taps, m)}
+            if self.cfg["demod"] == "c4fm":
+                st["procs"] = [oracle.OneChannelOutputProcessor(50000.0, k, float(m)) for k in range(m)]
+                st["chains"] = [oracle.P25Chain(oracle.C4FM, 50000.0, fir) for _ in range(m)]
+            self.states.append(st)
 
-    def one_pass(st):
-        res = st["chan"].receive(x)
-        if cfg["demod"] == "c4fm":
-            for k in range(m):
+    def one_pass(self, st):
+        res = st["chan"].receive(self.x)
+        if self.cfg["demod"] == "c4fm":
+            for k in range(self.m):
                 y = st["procs"][k].process(res)
                 st["chains"][k].receive(y[: y.size // 2048 * 2048])
+        else:
+            # the reference's per-channel extraction (ReusableChannelResultsBuffer.getChannel + gain) is part of
+            # configs[1]'s [channel][time] output
+            import oracle
+            if "procs" not in st:
+                st["procs"] = [oracle.OneChannelOutputProcessor(50000.0, k, float(self.m)) for k in range(self.m)]
+            for k in range(self.m):
+                st["procs"][k].process(res)
 
-    states = [make_state() for _ in range(threads)]
-    one_pass(states[0])                      # warm-up
-    t0 = time.perf_counter()
-    one_pass(states[0])
-    single = time.perf_counter() - t0
-    reps = max(1, int(target_seconds / max(single, 1e-3)))
-    done = [0] * threads
+    def run(self, reps, threads=None):
+        """all threads x reps passes; returns (seconds, complex input samples processed)"""
+        threads = threads or self.threads
+        ths = [threading.Thread(target=lambda s=self.states[i]: [self.one_pass(s) for _ in range(reps)])
+               for i in range(threads)]
+        t0 = time.perf_counter()
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+        return time.perf_counter() - t0, threads * reps * self.n_complex
 
-    def worker(i):
-        for _ in range(reps):
-            one_pass(states[i])
-            done[i] += 1
+    def describe(self, reps):
+        return ("%d threads x %d passes over %d complex input samples each (%s); oracle = C restatement of the "
+                "reference Java path, JVM unavailable" % (self.threads, reps, self.n_complex, self.workload))
 
-    ths = [threading.Thread(target=worker, args=(i,)) for i in range(threads)]
-    t0 = time.perf_counter()
-    for t in ths:
-        t.start()
-    for t in ths:
-        t.join()
-    dt = time.perf_counter() - t0
-    total = sum(done) * n_complex
+
+def cpu_baseline(workload, threads, target_seconds=10.0):
+    chain = CpuChain(workload, threads)
+    chain.run(1, 1)                                   # warm-up
+    single_s, n = chain.run(1, 1)
+    reps = max(1, int(target_seconds / max(single_s * 1.3, 1e-3)))
+    dt, total = chain.run(reps)
     return {"value": total / dt / 1e6, "unit": UNIT, "cores": threads, "kind": "port",
-            "single_thread_value": n_complex / single / 1e6,
-            "sample": "%d threads x %d passes over %d complex input samples each (%s); oracle = C restatement of "
-                      "the reference Java path, JVM unavailable" % (threads, reps, n_complex, workload)}
+            "single_thread_value": n / single_s / 1e6, "sample": chain.describe(reps)}
 
 
 # ---------------------------------------------------------------------------------------------- reference arm
 def run_reference(args, rank, world):
+    """Times the reference's CPU implementation of the path (the oracle port; the Java itself cannot run here:
+    no JVM) on all host threads.  One step = every thread runs `reps` passes over the bounded sample."""
     if rank != 0:
         return
     cores = os.cpu_count() or 1
     cfg = WORKLOADS[args.workload]
-    results = []
-    for _ in range(args.warmup + args.steps):
-        results.append(cpu_baseline(args.workload, cores, target_seconds=3.0))
-    timed = results[args.warmup:]
-    value = statistics.mean(r["value"] for r in timed)
-    base = timed[-1]
-    base["value"] = value
+    chain = CpuChain(args.workload, cores)
+    chain.run(1, 1)
+    single_s, _ = chain.run(1, 1)
+    reps = max(1, int(1.0 / max(single_s * 1.3, 1e-3)))     # ~1-2 s per step
+    for _ in range(args.warmup):
+        chain.run(reps)
+    dt, total = 0.0, 0
+    for _ in range(args.steps):
+        d, n = chain.run(reps)
+        dt += d
+        total += n
+    value = total / dt / 1e6
+    base = {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": chain.describe(reps)}
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": cfg["desc"]}, "cpu_baseline": base,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -202,70 +233,105 @@ def run_reference(args, rank, world):
 
 
 # ---------------------------------------------------------------------------------------------- GPU arm
-def run_gpu(args, rank, world, local_rank):
-    import torch
-    import torch.distributed as dist
-    from sdrtrunk_b200 import native
-    from sdrtrunk_b200.dsp import ComplexPolyphaseChannelizerM2
+class GpuWorkload:
+    """One workload's device state: synthetic input in HBM + pinned host copy, channelizer (+ bank + pipeline)."""
 
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    native.init(local_rank)
-    L = native.lib()
-    cfg = WORKLOADS[args.workload]
-    fs = cfg["fs"]
-    m = ComplexPolyphaseChannelizerM2.getChannelCount(fs)
-    n_complex = int(fs * cfg["seconds"]) // (1024 * (m // 2)) * (1024 * (m // 2)) if cfg["demod"] else int(fs * cfg["seconds"])
-    n_floats = 2 * n_complex
-    n_blocks = n_complex // (m // 2)
-    dev = torch.device("cuda", local_rank)
+    def __init__(self, name, rank, local_rank):
+        import torch
+        from sdrtrunk_b200 import native
+        from sdrtrunk_b200.dsp import Bank, ComplexPolyphaseChannelizerM2, Pipeline
+        self.torch, self.native, self.L = torch, native, native.lib()
+        self.name = name
+        self.cfg = cfg = WORKLOADS[name]
+        fs = cfg["fs"]
+        self.m = m = ComplexPolyphaseChannelizerM2.getChannelCount(fs)
+        n_complex = int(fs * cfg["seconds"])
+        if cfg["demod"]:
+            n_complex = n_complex // (1024 * (m // 2)) * (1024 * (m // 2))    # whole assembler buffers
+        self.n_complex, self.n_floats = n_complex, 2 * n_complex
+        self.n_blocks = n_complex // (m // 2)
+        self.dev = dev = torch.device("cuda", local_rank)
 
-    # synthetic tuner I/Q, generated on the device (tones on bin centres + AWGN), and its pinned host copy
-    g = torch.Generator(device=dev)
-    g.manual_seed(1234 + rank)
-    t = torch.arange(n_complex, device=dev, dtype=torch.float64)
-    z = 1e-3 * torch.randn(n_complex, 2, device=dev, generator=g, dtype=torch.float32)
-    for k in (3, 57, 123, 200, 277, 391):
-        f = (k if k < m // 2 else k - m) / m
-        ph = 2 * np.pi * ((f * t) % 1.0)
-        z[:, 0] += (0.05 * torch.cos(ph)).float()
-        z[:, 1] += (0.05 * torch.sin(ph)).float()
-    x_dev = z.reshape(-1).contiguous()
-    del t, z
-    x_host = torch.empty(n_floats, dtype=torch.float32, pin_memory=True)
-    x_host.copy_(x_dev)
+        # synthetic tuner I/Q generated on the device (tones near bin centres + AWGN), and its pinned host copy
+        g = torch.Generator(device=dev)
+        g.manual_seed(1234 + rank)
+        t = torch.arange(n_complex, device=dev, dtype=torch.float64)
+        z = 1e-3 * torch.randn(n_complex, 2, device=dev, generator=g, dtype=torch.float32)
+        for k in (3, 57, 123, 200, 277, 391):
+            f = (k if k < m // 2 else k - m) / m + 1e-5
+            ph = 2 * np.pi * ((f * t) % 1.0)
+            z[:, 0] += (0.05 * torch.cos(ph)).float()
+            z[:, 1] += (0.05 * torch.sin(ph)).float()
+        self.x_dev = z.reshape(-1).contiguous()
+        del t, z
+        self.x_host = torch.empty(self.n_floats, dtype=torch.float32, pin_memory=True)
+        self.x_host.copy_(self.x_dev)
 
-    stream = torch.cuda.Stream(device=dev)
-    chan = ComplexPolyphaseChannelizerM2(fs, cfg["taps_per_channel"], device=local_rank, maxInputFloats=n_floats)
-    chan.setStream(stream.cuda_stream)
-    out_dev = torch.empty((m, 2 * n_blocks), dtype=torch.float32, device=dev)
-    out_host = torch.empty((m, 2 * n_blocks), dtype=torch.float32, pin_memory=True)
-
-    pipeline = None
-    if cfg["demod"]:
-        from sdrtrunk_b200.dsp import P25Bank  # noqa: F401  (lands with the bank milestone)
-        pipeline = P25Bank.pipeline(chan, "c4fm", m, 50000.0, c4fm_fir_taps(), n_blocks, stream.cuda_stream)
-
-    def step_device():
-        if pipeline is None:
-            chan.receiveChannels((x_dev.data_ptr(), n_floats), native.DEVICE, out_dev.data_ptr(), native.DEVICE,
-                                 2 * n_blocks)
+        self.stream = torch.cuda.Stream(device=dev)
+        self.chan = ComplexPolyphaseChannelizerM2(fs, cfg["taps_per_channel"], device=local_rank,
+                                                  maxInputFloats=self.n_floats)
+        self.chan.setStream(self.stream.cuda_stream)
+        self.pipeline = None
+        if cfg["demod"] == "c4fm":
+            self.bank = Bank.preset(native.PRESET_P25_C4FM, m, 2 * fs / m, c4fm_fir_taps(),
+                                    max_samples_per_call=self.n_blocks, device=local_rank)
+            self.bank.setStream(self.stream.cuda_stream)
+            self.pipeline = Pipeline(self.chan, self.bank)
+            self.sym_stride = self.n_blocks // 8 + 64          # > 4800/50000 symbols per sample
+            self.sym_dev = torch.zeros((m, self.sym_stride), dtype=torch.uint8, device=dev)
+            self.cnt_dev = torch.zeros(m, dtype=torch.int32, device=dev)
+            self.sym_host = torch.zeros((m, self.sym_stride), dtype=torch.uint8, pin_memory=True)
+            self.cnt_host = torch.zeros(m, dtype=torch.int32, pin_memory=True)
+            self.h2d, self.d2h = 4 * self.n_floats, self.sym_host.numel() + 4 * m
         else:
-            pipeline.process_device(x_dev.data_ptr(), n_floats)
+            self.out_dev = torch.empty((m, 2 * self.n_blocks), dtype=torch.float32, device=dev)
+            self.out_host = torch.empty((m, 2 * self.n_blocks), dtype=torch.float32, pin_memory=True)
+            self.h2d, self.d2h = 4 * self.n_floats, self.out_host.numel() * 4
 
-    def step_host():
-        if pipeline is None:
-            native.check(L.sdrgpu_chan_process(chan._h, C.c_void_p(x_host.data_ptr()), n_floats, native.HOST,
-                                               C.c_void_p(out_host.data_ptr()), 2 * n_blocks, native.HOST,
-                                               native.LAYOUT_CHANNELS, None))
+    def step_device(self):
+        n, L = self.native, self.L
+        if self.pipeline is None:
+            n.check(L.sdrgpu_chan_process(self.chan._h, C.c_void_p(self.x_dev.data_ptr()), self.n_floats, n.DEVICE,
+                                          C.c_void_p(self.out_dev.data_ptr()), 2 * self.n_blocks, n.DEVICE,
+                                          n.LAYOUT_CHANNELS, None))
         else:
-            pipeline.process_host(x_host.data_ptr(), n_floats)
+            n.check(L.sdrgpu_pipeline_process(self.pipeline._h, C.c_void_p(self.x_dev.data_ptr()), self.n_floats,
+                                              n.DEVICE, C.c_void_p(self.sym_dev.data_ptr()), self.sym_stride, None, 0,
+                                              C.c_void_p(self.cnt_dev.data_ptr()), n.DEVICE))
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
+    def step_host(self):
+        n, L = self.native, self.L
+        if self.pipeline is None:
+            n.check(L.sdrgpu_chan_process(self.chan._h, C.c_void_p(self.x_host.data_ptr()), self.n_floats, n.HOST,
+                                          C.c_void_p(self.out_host.data_ptr()), 2 * self.n_blocks, n.HOST,
+                                          n.LAYOUT_CHANNELS, None))
+        else:
+            n.check(L.sdrgpu_pipeline_process(self.pipeline._h, C.c_void_p(self.x_host.data_ptr()), self.n_floats,
+                                              n.HOST, C.c_void_p(self.sym_host.data_ptr()), self.sym_stride, None, 0,
+                                              C.c_void_p(self.cnt_host.data_ptr()), n.HOST))
+
+    def kernel_times(self, steps):
+        """per-kernel device time, live, CUDA events on the launching stream (own loop so that the per-step event
+        synchronisation does not perturb the throughput numbers)"""
+        self.chan.enableTiming(True)
+        if self.pipeline is not None:
+            self.bank.enableTiming(True)
+        rows = []
+        for _ in range(steps):
+            self.step_device()
+            row = {"pfb_ifft": self.chan.lastKernelMs()}
+            if self.pipeline is not None:
+                f, d = self.bank.lastKernelMs()
+                row.update({"fir_agc": f, "psk": d})
+            rows.append(row)
+        self.chan.enableTiming(False)
+        if self.pipeline is not None:
+            self.bank.enableTiming(False)
+        return {k: statistics.mean(r[k] for r in rows) for k in rows[0]}
+
+
+def measure(w, args, world, dist, barrier):
+    torch, L = w.torch, w.L
 
     def timed(fn, steps, warmup):
         for _ in range(warmup):
@@ -273,85 +339,126 @@ def run_gpu(args, rank, world, local_rank):
         barrier()
         start = torch.cuda.Event(enable_timing=True)
         stop = torch.cuda.Event(enable_timing=True)
-        start.record(stream)
+        start.record(w.stream)
         t0 = time.perf_counter()
         for _ in range(steps):
             fn()
-        stop.record(stream)
+        stop.record(w.stream)
         barrier()
         wall = (time.perf_counter() - t0) * 1e3
         ms = start.elapsed_time(stop)
         if world > 1:
-            tt = torch.tensor([ms, wall], device=dev, dtype=torch.float64)
+            tt = torch.tensor([ms, wall], device=w.dev, dtype=torch.float64)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             ms, wall = tt.tolist()
         return ms, wall
 
+    launches0 = L.sdrgpu_launch_count()
+    ms_dev, _ = timed(w.step_device, args.steps, args.warmup)
+    launches = (L.sdrgpu_launch_count() - launches0) * args.steps // (args.steps + args.warmup)
+    # host-buffer path: device time of the stream also covers the copies; wall clock is what a caller sees
+    ms_e2e_dev, wall_e2e = timed(w.step_host, args.steps, max(3, args.warmup))
+    kernels = w.kernel_times(min(args.steps, 10))
+    ms_per_step = ms_dev / args.steps
+    total = w.n_complex * world
+    e2e_ms = max(ms_e2e_dev, wall_e2e) / args.steps
+    return {"ms_per_step": ms_per_step, "value": total / (ms_per_step * 1e-3) / 1e6,
+            "e2e_ms": e2e_ms, "e2e_value": total / (e2e_ms * 1e-3) / 1e6, "launches": launches, "kernels": kernels}
+
+
+def run_gpu(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from sdrtrunk_b200 import native
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    native.init(local_rank)
+    dev = torch.device("cuda", local_rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    peak, peak_src = load_peaks()
     sampler = ClockSampler(local_rank)
+    w = GpuWorkload(args.workload, rank, local_rank)
     if rank == 0:
         sampler.start()
-    launches0 = L.sdrgpu_launch_count()
-    ms_dev, _ = timed(step_device, args.steps, args.warmup)
-    launches = L.sdrgpu_launch_count() - launches0
-    launches_timed = launches * args.steps // (args.steps + args.warmup)
-    # host-buffer path: device time of the stream also covers the copies; wall clock is what a caller sees
-    ms_e2e_dev, wall_e2e = timed(step_host, args.steps, max(3, args.warmup))
+    r = measure(w, args, world, dist, barrier)
     clocks = sampler.stop() if rank == 0 else None
+    cfg, m, fs = w.cfg, w.m, w.cfg["fs"]
 
-    # dominant-kernel time, live, CUDA events on the launching stream (separate loop so the per-step event
-    # synchronisation does not perturb the numbers above)
-    kernel_ms = []
-    if pipeline is None:
-        chan.enableTiming(True)
-        for _ in range(args.steps):
-            step_device()
-            kernel_ms.append(chan.lastKernelMs())
-        chan.enableTiming(False)
-    else:
-        kernel_ms = pipeline.kernel_ms(step_device, args.steps)
+    def roofline_of(w, r):
+        # dominant kernel = the one with the largest share of the step
+        if w.pipeline is None:
+            alg = 24.0 * w.n_complex      # 8 B read + 16 B written per input complex sample, all M bins kept
+            k_ms = r["kernels"]["pfb_ifft"]
+            ach = alg / (k_ms * 1e-3) / 1e9
+            return {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "traffic": load_traffic("pfb_ifft_kernel"), "kernel": "pfb_ifft_kernel", "kernel_ms": k_ms,
+                    "algorithmic_bytes_per_launch": alg, "peak_source": peak_src}
+        # chain: report the serial timing-recovery kernel (latency bound) with the HBM bytes it moves, and the
+        # FP32 view of the FIR that feeds it
+        n_ch = w.n_blocks * m
+        k_ms = r["kernels"]["psk"]
+        alg = 8.0 * n_ch + n_ch * 4800.0 / 50000.0
+        ach = alg / (k_ms * 1e-3) / 1e9
+        fir_flop = n_ch * 72 * 4.0
+        return {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                "kernel": "psk_kernel", "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg,
+                "peak_source": peak_src, "note": "one warp per channel, latency bound by the per-symbol loop",
+                "kernels_ms": r["kernels"],
+                "fir_fp32": {"achieved_tflops": fir_flop / (r["kernels"]["fir_agc"] * 1e-3) / 1e12,
+                             "peak_tflops": FP32_PEAK_TFLOPS}}
+
+    main_roofline = roofline_of(w, r)
+    h2d, d2h = w.h2d, w.d2h
+    n_complex, n_blocks = w.n_complex, w.n_blocks
+    extra = None
+    if not args.no_extra and args.workload == "channelizer":
+        del w
+        torch.cuda.empty_cache()
+        w2 = GpuWorkload("c4fm", rank, local_rank)
+        r2 = measure(w2, args, world, dist, barrier)
+        extra = {"workload": w2.cfg["desc"], "value": r2["value"], "unit": UNIT, "ms_per_step": r2["ms_per_step"],
+                 "realtime_channels": m * world * (r2["value"] / world) / (fs / 1e6),
+                 "e2e": {"value": r2["e2e_value"], "unit": UNIT, "h2d_bytes_per_step": w2.h2d,
+                         "d2h_bytes_per_step": w2.d2h, "ms_per_step": r2["e2e_ms"]},
+                 "gpu_launches": r2["launches"], "kernels_ms": r2["kernels"], "roofline": roofline_of(w2, r2)}
+        del w2
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    ms_per_step = ms_dev / args.steps
-    total_samples = n_complex * world
-    value = total_samples / (ms_per_step * 1e-3) / 1e6
-    e2e_ms = max(ms_e2e_dev, wall_e2e) / args.steps
-    e2e_value = total_samples / (e2e_ms * 1e-3) / 1e6
-    peak, peak_src = load_peaks()
-    if pipeline is None:
-        alg_bytes = 24.0 * n_complex            # 8 B read + 16 B written per input complex sample, all M bins kept
-        k_ms = statistics.mean(kernel_ms)
-        achieved = alg_bytes / (k_ms * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": None, "kernel": "pfb_ifft_kernel<16,9>", "kernel_ms": k_ms,
-                    "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src}
-        h2d, d2h = 4 * n_floats, out_host.numel() * 4
-    else:
-        roofline, h2d, d2h = pipeline.roofline(kernel_ms, n_complex, peak, peak_src)
-
     cores = os.cpu_count() or 1
     base = cpu_baseline(args.workload, cores) if not args.no_cpu_baseline else None
+    if extra is not None and not args.no_cpu_baseline:
+        extra["cpu_baseline"] = cpu_baseline("c4fm", cores, target_seconds=8.0)
 
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
+        "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": cfg["desc"], "input_complex_samples_per_step_per_gpu": n_complex,
                    "channels": m, "channel_rate_hz": 2 * fs / m,
                    "l2": "per-step working set (%.0f MB in + %.0f MB out) exceeds the 126 MB L2" %
-                         (4 * n_floats / 1e6, out_dev.numel() * 4 / 1e6),
+                         (8 * n_complex / 1e6, 8.0 * m * n_blocks / 1e6),
                    "sharding": "one independent tuner stream per GPU, no collective"},
-        "realtime_channels": m * world * (value / world) / (fs / 1e6),
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_ms},
-        "gpu_launches": launches_timed,
-        "roofline": roofline,
+        "realtime_channels": m * world * (r["value"] / world) / (fs / 1e6),
+        "e2e": {"value": r["e2e_value"], "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": r["e2e_ms"]},
+        "gpu_launches": r["launches"],
+        "roofline": main_roofline,
         "cpu_baseline": base,
         "clocks": clocks,
     }
+    if extra is not None:
+        line["chain_c4fm"] = extra
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -365,6 +472,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="channelizer", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary configs[2] chain measurement")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
