@@ -232,6 +232,77 @@ def run_reference(args, rank, world):
     print(json.dumps(line))
 
 
+
+# ---------------------------------------------------------------------------------------------- GPU-side synthetic input
+def synth_tones_wideband(torch, dev, m, n_complex, seed):
+    """one unit-phase-random tone per bin at bin centre + U(-5, 5) kHz, amplitude 1/M each,
+    plus AWGN sigma 1e-4 per axis.  Built in the frequency domain (tones on FFT bins of the n_complex-point grid)."""
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    spec = torch.zeros(n_complex, dtype=torch.complex64, device=dev)
+    k = torch.arange(m, device=dev)
+    centre = torch.where(k < m // 2, k, k - m).double() / m                       # cycles per sample
+    off = (torch.rand(m, device=dev, generator=g, dtype=torch.float64) - 0.5) * (10000.0 / (25000.0 * m))
+    bins = torch.round((centre + off) * n_complex).long() % n_complex
+    ph = 2 * np.pi * torch.rand(m, device=dev, generator=g, dtype=torch.float64)
+    spec[bins] = torch.polar(torch.full((m,), float(n_complex) / m, device=dev, dtype=torch.float64), ph).to(torch.complex64)
+    z = torch.fft.ifft(spec)
+    del spec
+    x = torch.view_as_real(z).reshape(-1).contiguous()
+    x += 1e-4 * torch.randn(x.shape, device=dev, generator=g, dtype=torch.float32)
+    return x
+
+
+def synth_c4fm_wideband(torch, dev, m, n_ch, seed, amplitude=0.02, noise=2e-3):
+    """every bin carries a continuous C4FM stream (4800 sym/s, deviation levels +/-1, +/-3 ->
+    phase steps of level * pi/4 per symbol, raised-cosine frequency pulses), random dibits, carrier offset U(-200, 200)
+    Hz and timing phase per channel; channels are multiplexed onto the bin centres in the frequency domain."""
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    fs_ch, sym_rate = 50000.0, 4800.0
+    sps = fs_ch / sym_rate
+    n_sym = int(n_ch / sps) + 8
+    dibits = torch.randint(0, 4, (m, n_sym), device=dev, generator=g)
+    levels = torch.tensor([1.0, 3.0, -1.0, -3.0], device=dev, dtype=torch.float64)[dibits]
+    off = (torch.rand(m, 1, device=dev, generator=g, dtype=torch.float64) - 0.5) * 400.0
+    tphase = torch.rand(m, 1, device=dev, generator=g, dtype=torch.float64)
+    phase0 = 2 * np.pi * torch.rand(m, 1, device=dev, generator=g, dtype=torch.float64)
+    n = torch.arange(n_ch, device=dev, dtype=torch.float64).unsqueeze(0)
+    n_w = n_ch * m // 2
+    spec = torch.zeros(n_w, dtype=torch.complex64, device=dev)
+    quarter = n_ch // 4
+    j = torch.cat([torch.arange(0, quarter, device=dev), torch.arange(-quarter, 0, device=dev)])
+    for lo in range(0, m, 50):                       # 50 channels at a time bounds the float64 temporaries
+        hi = min(m, lo + 50)
+        t = n / sps - tphase[lo:hi]
+        k = torch.floor(t).long()
+        valid = (k >= 0) & (k < n_sym)
+        u = t - k - 0.5
+        pulse = 1.0 + torch.cos(2 * np.pi * u)
+        lv = torch.gather(levels[lo:hi], 1, k.clamp(0, n_sym - 1))
+        freq = torch.where(valid, lv * pulse, torch.zeros_like(pulse))
+        phase = torch.cumsum(freq, dim=1) * (np.pi / 4.0) / sps + 2 * np.pi * off[lo:hi] * n / fs_ch + phase0[lo:hi]
+        xf = torch.fft.fft(torch.polar(torch.full_like(phase, amplitude), phase).to(torch.complex64), dim=1)
+        for c in range(lo, hi):
+            centre = (c if c < m // 2 else c - m) * (n_ch // 2)
+            spec[(centre + j) % n_w] += xf[c - lo, j % n_ch]
+        del t, k, valid, u, pulse, lv, freq, phase, xf
+    z = torch.fft.ifft(spec) * (n_w / n_ch)
+    del spec
+    x = torch.view_as_real(z).reshape(-1).contiguous()
+    x += noise * torch.randn(x.shape, device=dev, generator=g, dtype=torch.float32)
+    return x, dibits.to(torch.uint8).cpu().numpy()
+
+
+def dibit_match(decoded, truth, skip=300):
+    """fraction of decoded dibits equal to the transmitted ones after acquisition, best over small lags"""
+    best = 0.0
+    for lag in range(0, 24):
+        n = min(decoded.size - lag, truth.size) - 20
+        if n > skip + 100:
+            best = max(best, float(np.mean(decoded[lag + skip:lag + n] == truth[skip:n])))
+    return best
+
 # ---------------------------------------------------------------------------------------------- GPU arm
 class GpuWorkload:
     """One workload's device state: synthetic input in HBM + pinned host copy, channelizer (+ bank + pipeline)."""
@@ -252,18 +323,12 @@ class GpuWorkload:
         self.n_blocks = n_complex // (m // 2)
         self.dev = dev = torch.device("cuda", local_rank)
 
-        # synthetic tuner I/Q generated on the device (tones near bin centres + AWGN), and its pinned host copy
-        g = torch.Generator(device=dev)
-        g.manual_seed(1234 + rank)
-        t = torch.arange(n_complex, device=dev, dtype=torch.float64)
-        z = 1e-3 * torch.randn(n_complex, 2, device=dev, generator=g, dtype=torch.float32)
-        for k in (3, 57, 123, 200, 277, 391):
-            f = (k if k < m // 2 else k - m) / m + 1e-5
-            ph = 2 * np.pi * ((f * t) % 1.0)
-            z[:, 0] += (0.05 * torch.cos(ph)).float()
-            z[:, 1] += (0.05 * torch.sin(ph)).float()
-        self.x_dev = z.reshape(-1).contiguous()
-        del t, z
+        # synthetic tuner I/Q generated on the device, and its pinned host copy
+        self.truth = None
+        if cfg["demod"] == "c4fm":
+            self.x_dev, self.truth = synth_c4fm_wideband(torch, dev, m, self.n_blocks, seed=3 + 1000 * rank)
+        else:
+            self.x_dev = synth_tones_wideband(torch, dev, m, n_complex, seed=2 + 1000 * rank)
         self.x_host = torch.empty(self.n_floats, dtype=torch.float32, pin_memory=True)
         self.x_host.copy_(self.x_dev)
 
@@ -310,6 +375,19 @@ class GpuWorkload:
                                               n.HOST, C.c_void_p(self.sym_host.data_ptr()), self.sym_stride, None, 0,
                                               C.c_void_p(self.cnt_host.data_ptr()), n.HOST))
 
+    def sanity(self):
+        """decoded-vs-transmitted dibits of a few channels (first pass from reset state would be needed for an exact
+        check; this is a plausibility figure for the timed workload, parity itself is tests/)"""
+        if self.truth is None:
+            return None
+        self.step_host()
+        cnt = self.cnt_host.numpy()
+        out = {}
+        for c in (0, 57, 200, 399):
+            dec = self.sym_host.numpy()[c, :cnt[c]]
+            out[str(c)] = {"symbols": int(cnt[c]), "match_after_acquisition": round(dibit_match(dec, self.truth[c]), 4)}
+        return out
+
     def kernel_times(self, steps):
         """per-kernel device time, live, CUDA events on the launching stream (own loop so that the per-step event
         synchronisation does not perturb the throughput numbers)"""
@@ -353,6 +431,7 @@ def measure(w, args, world, dist, barrier):
             ms, wall = tt.tolist()
         return ms, wall
 
+    sanity = w.sanity()          # first pass over the stream, from the reset state
     launches0 = L.sdrgpu_launch_count()
     ms_dev, _ = timed(w.step_device, args.steps, args.warmup)
     launches = (L.sdrgpu_launch_count() - launches0) * args.steps // (args.steps + args.warmup)
@@ -363,7 +442,8 @@ def measure(w, args, world, dist, barrier):
     total = w.n_complex * world
     e2e_ms = max(ms_e2e_dev, wall_e2e) / args.steps
     return {"ms_per_step": ms_per_step, "value": total / (ms_per_step * 1e-3) / 1e6,
-            "e2e_ms": e2e_ms, "e2e_value": total / (e2e_ms * 1e-3) / 1e6, "launches": launches, "kernels": kernels}
+            "e2e_ms": e2e_ms, "e2e_value": total / (e2e_ms * 1e-3) / 1e6, "launches": launches, "kernels": kernels,
+            "sanity": sanity}
 
 
 def run_gpu(args, rank, world, local_rank):
@@ -427,7 +507,8 @@ def run_gpu(args, rank, world, local_rank):
                  "realtime_channels": m * world * (r2["value"] / world) / (fs / 1e6),
                  "e2e": {"value": r2["e2e_value"], "unit": UNIT, "h2d_bytes_per_step": w2.h2d,
                          "d2h_bytes_per_step": w2.d2h, "ms_per_step": r2["e2e_ms"]},
-                 "gpu_launches": r2["launches"], "kernels_ms": r2["kernels"], "roofline": roofline_of(w2, r2)}
+                 "gpu_launches": r2["launches"], "kernels_ms": r2["kernels"], "roofline": roofline_of(w2, r2),
+                 "decode_sanity": r2["sanity"]}
         del w2
 
     if rank != 0:
@@ -457,6 +538,8 @@ def run_gpu(args, rank, world, local_rank):
         "cpu_baseline": base,
         "clocks": clocks,
     }
+    if r.get("sanity") is not None:
+        line["decode_sanity"] = r["sanity"]
     if extra is not None:
         line["chain_c4fm"] = extra
     print(json.dumps(line))
