@@ -27,6 +27,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "fft_regs.cuh"
 
 using namespace sdrgpu;
 
@@ -40,6 +41,7 @@ struct ChanParams {
     const float2 *in;     // [n_in] new samples
     const float *taps;    // [M*T] prototype filter h
     const float2 *tw;     // [M] e^{+j 2 pi k / M}
+    const float2 *tw2;    // [R1][R2] e^{+j 2 pi n2 k1 / M}: the twiddles between the two steps of pfb2_kernel
     float *out;
     const int *sel;       // [n_sel] bin of each output row (channel layout)
     const float *gain_f;  // [n_sel] float gain (used when gain_exact)
@@ -253,6 +255,176 @@ __global__ void __launch_bounds__(kThreads) pfb_ifft_kernel(const ChanParams p)
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// pfb2_kernel: the fast path for channel counts that split as M = R1 * R2 with register-sized factors
+// (400 = 20 x 20, 800 = 32 x 25, 96 = 8 x 12).  One CTA per tile of NB consecutive blocks:
+//   1. filter bank (as above: thread <-> input offset r, taps in registers, NB blocks of two branches accumulated
+//      in registers, products rounded and added in tap order like the Java)         -> V[b][n]         (shared)
+//   2. step A: thread (b, n2) runs an R1-point DFT over n1 of V[b][R2 n1 + n2] in registers, multiplies by
+//      W_M^{n2 k1}                                                                  -> Y[b][k1][n2]    (shared)
+//   3. step B: thread (b, k1) runs an R2-point DFT over n2 in registers: bin k1 + R1 k2 -> X[k][b]     (shared)
+//   4. per-channel rows of NB consecutive samples (one 128-byte line for NB = 16) -> HBM, scaled by 1/M and the gain
+// Shared-memory traffic is 6 passes over the tile instead of 10 for the radix-4/5 Stockham version, and the index
+// arithmetic is compile-time.  Row strides: V rows M + 4 (== 4 mod 16 float2: the two half-warps of a 64-bit access
+// that straddle two rows hit disjoint banks), Y rows padded to an odd number of 16-byte slots (conflict-free
+// LDS.128), X rows NB + 1.
+// ---------------------------------------------------------------------------------------------------------------
+template <int R2>
+struct YPad {
+    static constexpr int even = (R2 + 1) & ~1;
+    static constexpr int value = ((even / 2) & 1) ? even : even + 2;   // float2 per (b, k1) row
+};
+
+template <int M, int R1, int R2, int NB, int TT, int NT>
+struct Pfb2Layout {
+    static constexpr int SV = M + 4;
+    static constexpr int LDX = NB + 1;
+    static constexpr int R2P = YPad<R2>::value;
+    static constexpr int YB = R1 * R2P;
+    static constexpr int region0 = (NB * SV > M * LDX) ? NB * SV : M * LDX;
+    static constexpr size_t smem_bytes = sizeof(float2) * (size_t)(region0 + NB * YB);
+};
+
+template <int M, int NB, int TT, bool FAST>
+__device__ __forceinline__ void fb_thread(const ChanParams &p, const float2 *__restrict__ xin, int b0, int r, float2 *V,
+                                          int SV)
+{
+    constexpr int half = M / 2;
+    const int n = half - 1 - r;
+    float hA[TT], hB[TT];
+#pragma unroll
+    for (int t = 0; t < TT; t++) {
+        hA[t] = __ldg(p.taps + n + t * M);
+        hB[t] = __ldg(p.taps + n + half + t * M);
+    }
+    float2 accA[NB], accB[NB];
+#pragma unroll
+    for (int pp = NB - 1; pp >= -(2 * TT - 1); --pp) {
+        const float2 x = FAST ? __ldg(xin + (pp + 2 * TT - 1) * half + r) : load_x(p, b0 + pp, r);
+#pragma unroll
+        for (int t = 0; t < TT; t++) {
+            const int bl = pp + 2 * t;  // branch n: unit P = B - 2t
+            if (bl >= 0 && bl < NB) {
+                const float px = __fmul_rn(x.x, hA[t]), py = __fmul_rn(x.y, hA[t]);
+                if (t == 0) accA[bl] = make_float2(__fadd_rn(0.0f, px), __fadd_rn(0.0f, py));
+                else accA[bl] = make_float2(__fadd_rn(accA[bl].x, px), __fadd_rn(accA[bl].y, py));
+            }
+            const int bm = pp + 1 + 2 * t;  // branch n + M/2: unit P = B - 1 - 2t
+            if (bm >= 0 && bm < NB) {
+                const float px = __fmul_rn(x.x, hB[t]), py = __fmul_rn(x.y, hB[t]);
+                if (t == 0) accB[bm] = make_float2(__fadd_rn(0.0f, px), __fadd_rn(0.0f, py));
+                else accB[bm] = make_float2(__fadd_rn(accB[bm].x, px), __fadd_rn(accB[bm].y, py));
+            }
+        }
+    }
+    const int par = (p.parity0 + b0) & 1;
+#pragma unroll
+    for (int bl = 0; bl < NB; bl++) {
+        const int odd = (par + bl) & 1;   // "middle" blocks: the two halves swap (the M/2 circular shift)
+        V[bl * SV + (odd ? n + half : n)] = accA[bl];
+        V[bl * SV + (odd ? n : n + half)] = accB[bl];
+    }
+}
+
+template <int M, int R1, int R2, int NB, int TT, int NT>
+__global__ void __launch_bounds__(NT, 2) pfb2_kernel(const ChanParams p)
+{
+    using L = Pfb2Layout<M, R1, R2, NB, TT, NT>;
+    constexpr int half = M / 2, SV = L::SV, LDX = L::LDX, R2P = L::R2P, YB = L::YB;
+    extern __shared__ __align__(16) float2 smem[];
+    float2 *V = smem;                 // [NB][SV], later X [M][LDX]
+    float2 *Y = smem + L::region0;    // [NB][R1][R2P]
+    const int tid = threadIdx.x;
+    const int b0 = blockIdx.x * NB;
+
+    // ------------------------------------------------------------------ 1. filter bank
+    {
+        // every sample this tile needs lies in the new input (true for all but the first tiles of a call)
+        const long long first = (long long)b0 * half - p.state_len;                    // index into p.in of unit b0-(2T-1)
+        const bool fast = first >= 0 && first + (long long)(NB + 2 * TT - 1) * half <= p.n_in;
+        const float2 *xin = p.in + (fast ? first : 0);
+        if (fast) {
+            for (int r = tid; r < half; r += NT) fb_thread<M, NB, TT, true>(p, xin, b0, r, V, SV);
+        } else {
+            for (int r = tid; r < half; r += NT) fb_thread<M, NB, TT, false>(p, xin, b0, r, V, SV);
+        }
+    }
+    __syncthreads();
+
+    // ------------------------------------------------------------------ 2. step A: R1-point DFTs over n1
+    for (int item = tid; item < NB * R2; item += NT) {
+        const int b = item / R2, n2 = item - b * R2;
+        float2 a[R1];
+        const float2 *v = V + b * SV + n2;
+#pragma unroll
+        for (int n1 = 0; n1 < R1; n1++) a[n1] = v[R2 * n1];
+        rfft::dft<R1>(a);
+        float2 *y = Y + b * YB + n2;
+        y[0] = a[0];
+#pragma unroll
+        for (int k1 = 1; k1 < R1; k1++) {
+            const float2 w = __ldg(p.tw2 + k1 * R2 + n2);
+            y[k1 * R2P] = rfft::cmul(a[k1], w.x, w.y);
+        }
+    }
+    __syncthreads();
+
+    // ------------------------------------------------------------------ 3. step B: R2-point DFTs over n2
+    float2 *X = V;
+    for (int item = tid; item < NB * R1; item += NT) {
+        const int b = item / R1, k1 = item - b * R1;
+        float2 a[R2];
+        const float4 *y = reinterpret_cast<const float4 *>(Y + b * YB + k1 * R2P);
+#pragma unroll
+        for (int i = 0; i < R2 / 2; i++) {
+            const float4 v = y[i];
+            a[2 * i] = make_float2(v.x, v.y);
+            a[2 * i + 1] = make_float2(v.z, v.w);
+        }
+        if (R2 & 1) a[R2 - 1] = Y[b * YB + k1 * R2P + R2 - 1];
+        rfft::dft<R2>(a);
+#pragma unroll
+        for (int k2 = 0; k2 < R2; k2++) X[(k1 + R1 * k2) * LDX + b] = a[k2];
+    }
+    __syncthreads();
+
+    // ------------------------------------------------------------------ 4. scale + store
+    const float inv_m = p.inv_m;
+    if (p.layout == SDRGPU_LAYOUT_CHANNELS) {
+        const int total = p.n_sel * NB;
+        for (int i = tid; i < total; i += NT) {
+            const int bl = i % NB, c = i / NB;
+            const int b = b0 + bl;
+            if (b >= p.n_blocks) continue;
+            float2 v = X[__ldg(p.sel + c) * LDX + bl];
+            v.x = __fmul_rn(v.x, inv_m);  // FloatFFT_1D.complexInverse(a, true): a[i] *= 1.0f / n
+            v.y = __fmul_rn(v.y, inv_m);
+            if (p.gain_exact) {  // float * float == (float)(float * double) when the gain is float-representable
+                const float g = __ldg(p.gain_f + c);
+                v.x = __fmul_rn(v.x, g);
+                v.y = __fmul_rn(v.y, g);
+            } else {  // ReusableComplexBuffer.applyGain: samples[x] *= (double)gain
+                const double g = __ldg(p.gain_d + c);
+                v.x = __double2float_rn(__dmul_rn((double)v.x, g));
+                v.y = __double2float_rn(__dmul_rn((double)v.y, g));
+            }
+            *reinterpret_cast<float2 *>(p.out + (size_t)c * p.out_stride + 2 * (size_t)b) = v;
+        }
+    } else {
+        const int total = M * NB;
+        for (int i = tid; i < total; i += NT) {
+            const int k = i % M, bl = i / M;
+            const int b = b0 + bl;
+            if (b >= p.n_blocks) continue;
+            float2 v = X[k * LDX + bl];
+            v.x = __fmul_rn(v.x, inv_m);
+            v.y = __fmul_rn(v.y, inv_m);
+            *reinterpret_cast<float2 *>(p.out + ((size_t)b * M + k) * 2) = v;
+        }
+    }
+}
+
 // new_state[i] = S[consumed + i], S = [state | in]
 __global__ void save_state_kernel(const float2 *state, int state_len, const float2 *in, int n_in, int consumed,
                                   float2 *new_state, int new_len)
@@ -277,6 +449,8 @@ struct sdrgpu_channelizer {
     cudaStream_t own_stream = nullptr, stream = nullptr;
     float *d_taps = nullptr;
     float2 *d_tw = nullptr;
+    float2 *d_tw2 = nullptr;   // pfb2_kernel inter-step twiddles
+    int fast_r1 = 0, fast_r2 = 0;  // factors of the pfb2 fast path (0 = generic kernel)
     float2 *d_state[2] = {nullptr, nullptr};
     int cur_state = 0;
     float2 *d_in = nullptr;    // staging for host input
@@ -323,6 +497,19 @@ sdrgpu_status upload_selection(sdrgpu_channelizer *h)
     SDRGPU_CUDA(cudaMemcpy(h->d_gain_d, gd.data(), sizeof(double) * (size_t)n, cudaMemcpyHostToDevice));
     h->n_sel = n;
     h->gain_exact = exact;
+    return SDRGPU_OK;
+}
+
+template <int M, int R1, int R2, int NB, int TT, int NT>
+sdrgpu_status launch_pfb2(const sdrgpu_channelizer *h, const ChanParams &p)
+{
+    using L = Pfb2Layout<M, R1, R2, NB, TT, NT>;
+    auto kernel = pfb2_kernel<M, R1, R2, NB, TT, NT>;
+    SDRGPU_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::smem_bytes));
+    const int grid = (p.n_blocks + NB - 1) / NB;
+    kernel<<<grid, NT, L::smem_bytes, h->stream>>>(p);
+    count_launch();
+    SDRGPU_CUDA(cudaGetLastError());
     return SDRGPU_OK;
 }
 
@@ -421,6 +608,22 @@ sdrgpu_status sdrgpu_chan_create(sdrgpu_channelizer **out, const float *taps, in
     CHK(cudaMemcpy(h->d_taps, padded.data(), sizeof(float) * padded.size(), cudaMemcpyHostToDevice));
     CHK(cudaMalloc(&h->d_tw, sizeof(float2) * (size_t)M));
     CHK(cudaMemcpy(h->d_tw, tw.data(), sizeof(float2) * (size_t)M, cudaMemcpyHostToDevice));
+    // fast path (pfb2_kernel) for the channel counts of the common tuner rates with the reference's 9 taps per channel
+    if (h->T == 9) {
+        if (M == 400) { h->fast_r1 = 20; h->fast_r2 = 20; }
+        else if (M == 800) { h->fast_r1 = 32; h->fast_r2 = 25; }
+        else if (M == 96) { h->fast_r1 = 8; h->fast_r2 = 12; }
+    }
+    if (h->fast_r1) {
+        std::vector<float2> tw2((size_t)M);
+        for (int k1 = 0; k1 < h->fast_r1; k1++)
+            for (int n2 = 0; n2 < h->fast_r2; n2++) {
+                const double a = 2.0 * 3.14159265358979323846 * (double)((long long)k1 * n2 % M) / (double)M;
+                tw2[(size_t)k1 * h->fast_r2 + n2] = make_float2((float)cos(a), (float)sin(a));
+            }
+        CHK(cudaMalloc(&h->d_tw2, sizeof(float2) * (size_t)M));
+        CHK(cudaMemcpy(h->d_tw2, tw2.data(), sizeof(float2) * (size_t)M, cudaMemcpyHostToDevice));
+    }
     const size_t state_cap = (size_t)h->H + h->half;
     for (int i = 0; i < 2; i++) {
         CHK(cudaMalloc(&h->d_state[i], sizeof(float2) * state_cap));
@@ -441,6 +644,7 @@ sdrgpu_status sdrgpu_chan_destroy(sdrgpu_channelizer *h)
     if (h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->d_taps);
     cudaFree(h->d_tw);
+    cudaFree(h->d_tw2);
     cudaFree(h->d_state[0]);
     cudaFree(h->d_state[1]);
     cudaFree(h->d_in);
@@ -572,6 +776,7 @@ sdrgpu_status sdrgpu_chan_process(sdrgpu_channelizer *h, const float *iq, int n_
         p.in = d_in;
         p.taps = h->d_taps;
         p.tw = h->d_tw;
+        p.tw2 = h->d_tw2;
         p.out = d_out;
         p.sel = h->d_sel;
         p.gain_f = h->d_gain_f;
@@ -597,7 +802,10 @@ sdrgpu_status sdrgpu_chan_process(sdrgpu_channelizer *h, const float *iq, int n_
         const int grid = (n_blocks + h->NB - 1) / h->NB;
         h->timer.begin(h->stream);
         sdrgpu_status st;
-        if (h->NB == 16) st = (h->T == 9) ? launch_pfb<16, 9>(h, p, grid) : launch_pfb<16, 0>(h, p, grid);
+        if (h->fast_r1 && h->M == 400) st = launch_pfb2<400, 20, 20, 16, 9, 320>(h, p);
+        else if (h->fast_r1 && h->M == 800) st = launch_pfb2<800, 32, 25, 8, 9, 256>(h, p);
+        else if (h->fast_r1 && h->M == 96) st = launch_pfb2<96, 8, 12, 16, 9, 192>(h, p);
+        else if (h->NB == 16) st = (h->T == 9) ? launch_pfb<16, 9>(h, p, grid) : launch_pfb<16, 0>(h, p, grid);
         else st = (h->T == 9) ? launch_pfb<8, 9>(h, p, grid) : launch_pfb<8, 0>(h, p, grid);
         h->timer.end(h->stream);
         SDRGPU_TRY(st);
