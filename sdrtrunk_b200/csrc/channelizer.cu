@@ -24,6 +24,7 @@
 // 128-byte line for NB = 16) are bank-conflict free and coalesced.
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
@@ -51,6 +52,8 @@ struct ChanParams {
     int M, T, half, H;
     int n_blocks, parity0;
     int n_sel, layout, gain_exact;
+    int identity;        // selection is every bin in order with one float-representable gain (gain_uniform)
+    float gain_uniform;
     float inv_m;
     int n_factors;
     int factors[kMaxFactors];
@@ -307,13 +310,14 @@ __device__ __forceinline__ void fb_thread(const ChanParams &p, const float2 *__r
             const int bl = pp + 2 * t;  // branch n: unit P = B - 2t
             if (bl >= 0 && bl < NB) {
                 const float px = __fmul_rn(x.x, hA[t]), py = __fmul_rn(x.y, hA[t]);
-                if (t == 0) accA[bl] = make_float2(__fadd_rn(0.0f, px), __fadd_rn(0.0f, py));
+                // (the Java's 0.0f + product differs from the product only in the sign of a zero)
+                if (t == 0) accA[bl] = make_float2(px, py);
                 else accA[bl] = make_float2(__fadd_rn(accA[bl].x, px), __fadd_rn(accA[bl].y, py));
             }
             const int bm = pp + 1 + 2 * t;  // branch n + M/2: unit P = B - 1 - 2t
             if (bm >= 0 && bm < NB) {
                 const float px = __fmul_rn(x.x, hB[t]), py = __fmul_rn(x.y, hB[t]);
-                if (t == 0) accB[bm] = make_float2(__fadd_rn(0.0f, px), __fadd_rn(0.0f, py));
+                if (t == 0) accB[bm] = make_float2(px, py);
                 else accB[bm] = make_float2(__fadd_rn(accB[bm].x, px), __fadd_rn(accB[bm].y, py));
             }
         }
@@ -327,8 +331,8 @@ __device__ __forceinline__ void fb_thread(const ChanParams &p, const float2 *__r
     }
 }
 
-template <int M, int R1, int R2, int NB, int TT, int NT>
-__global__ void __launch_bounds__(NT, 2) pfb2_kernel(const ChanParams p)
+template <int M, int R1, int R2, int NB, int TT, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) pfb2_kernel(const ChanParams p)
 {
     using L = Pfb2Layout<M, R1, R2, NB, TT, NT>;
     constexpr int half = M / 2, SV = L::SV, LDX = L::LDX, R2P = L::R2P, YB = L::YB;
@@ -390,26 +394,54 @@ __global__ void __launch_bounds__(NT, 2) pfb2_kernel(const ChanParams p)
     __syncthreads();
 
     // ------------------------------------------------------------------ 4. scale + store
+    // FloatFFT_1D.complexInverse(a, true): a[i] *= 1.0f / n; then ReusableComplexBuffer.applyGain: samples[x] *= gain
+    // (a double; float * float == (float)(float * double) when the gain is float-representable: gain_exact)
     const float inv_m = p.inv_m;
     if (p.layout == SDRGPU_LAYOUT_CHANNELS) {
-        const int total = p.n_sel * NB;
-        for (int i = tid; i < total; i += NT) {
-            const int bl = i % NB, c = i / NB;
-            const int b = b0 + bl;
-            if (b >= p.n_blocks) continue;
-            float2 v = X[__ldg(p.sel + c) * LDX + bl];
-            v.x = __fmul_rn(v.x, inv_m);  // FloatFFT_1D.complexInverse(a, true): a[i] *= 1.0f / n
-            v.y = __fmul_rn(v.y, inv_m);
-            if (p.gain_exact) {  // float * float == (float)(float * double) when the gain is float-representable
-                const float g = __ldg(p.gain_f + c);
-                v.x = __fmul_rn(v.x, g);
-                v.y = __fmul_rn(v.y, g);
-            } else {  // ReusableComplexBuffer.applyGain: samples[x] *= (double)gain
-                const double g = __ldg(p.gain_d + c);
-                v.x = __double2float_rn(__dmul_rn((double)v.x, g));
-                v.y = __double2float_rn(__dmul_rn((double)v.y, g));
+        // NB consecutive lanes write the NB consecutive samples of one channel row (128 bytes for NB = 16)
+        constexpr int ROWS = NT / NB;                  // channel rows per pass over the CTA
+        const int bl = tid % NB, row0 = tid / NB;
+        const int b = b0 + bl;
+        if (tid < ROWS * NB && b < p.n_blocks) {
+            float *out = p.out + 2 * (size_t)b;
+            if (p.identity) {
+                // default selection: every bin in order, one float-representable gain
+                const float g = p.gain_uniform;
+                const float2 *xr = X + row0 * LDX + bl;
+                float *o = out + (size_t)row0 * p.out_stride;
+                const size_t ostep = (size_t)ROWS * p.out_stride;
+                constexpr int ITER = M / ROWS;          // whole passes; the remainder rows follow
+#pragma unroll 5
+                for (int it = 0; it < ITER; it++) {
+                    float2 v = xr[it * ROWS * LDX];
+                    v.x = __fmul_rn(__fmul_rn(v.x, inv_m), g);
+                    v.y = __fmul_rn(__fmul_rn(v.y, inv_m), g);
+                    *reinterpret_cast<float2 *>(o) = v;
+                    o += ostep;
+                }
+                if (ITER * ROWS + row0 < M) {
+                    float2 v = xr[ITER * ROWS * LDX];
+                    v.x = __fmul_rn(__fmul_rn(v.x, inv_m), g);
+                    v.y = __fmul_rn(__fmul_rn(v.y, inv_m), g);
+                    *reinterpret_cast<float2 *>(o) = v;
+                }
+            } else if (p.gain_exact) {
+                for (int c = row0; c < p.n_sel; c += ROWS) {
+                    const float g = __ldg(p.gain_f + c);
+                    float2 v = X[__ldg(p.sel + c) * LDX + bl];
+                    v.x = __fmul_rn(__fmul_rn(v.x, inv_m), g);
+                    v.y = __fmul_rn(__fmul_rn(v.y, inv_m), g);
+                    *reinterpret_cast<float2 *>(out + (size_t)c * p.out_stride) = v;
+                }
+            } else {
+                for (int c = row0; c < p.n_sel; c += ROWS) {
+                    const double g = __ldg(p.gain_d + c);
+                    float2 v = X[__ldg(p.sel + c) * LDX + bl];
+                    v.x = __double2float_rn(__dmul_rn((double)__fmul_rn(v.x, inv_m), g));
+                    v.y = __double2float_rn(__dmul_rn((double)__fmul_rn(v.y, inv_m), g));
+                    *reinterpret_cast<float2 *>(out + (size_t)c * p.out_stride) = v;
+                }
             }
-            *reinterpret_cast<float2 *>(p.out + (size_t)c * p.out_stride + 2 * (size_t)b) = v;
         }
     } else {
         const int total = M * NB;
@@ -461,6 +493,8 @@ struct sdrgpu_channelizer {
     float *d_gain_f = nullptr;
     double *d_gain_d = nullptr;
     int gain_exact = 1;
+    int identity = 0;
+    float gain_uniform = 0.0f;
     std::vector<sdrgpu_output_channel> channels;
     std::vector<int> factors;
     std::vector<unsigned> magic;
@@ -497,14 +531,18 @@ sdrgpu_status upload_selection(sdrgpu_channelizer *h)
     SDRGPU_CUDA(cudaMemcpy(h->d_gain_d, gd.data(), sizeof(double) * (size_t)n, cudaMemcpyHostToDevice));
     h->n_sel = n;
     h->gain_exact = exact;
+    h->identity = exact && n == h->M;
+    for (int i = 0; i < n && h->identity; i++)
+        if (sel[i] != i || gf[i] != gf[0]) h->identity = 0;
+    h->gain_uniform = n > 0 ? gf[0] : 0.0f;
     return SDRGPU_OK;
 }
 
-template <int M, int R1, int R2, int NB, int TT, int NT>
+template <int M, int R1, int R2, int NB, int TT, int NT, int MINB>
 sdrgpu_status launch_pfb2(const sdrgpu_channelizer *h, const ChanParams &p)
 {
     using L = Pfb2Layout<M, R1, R2, NB, TT, NT>;
-    auto kernel = pfb2_kernel<M, R1, R2, NB, TT, NT>;
+    auto kernel = pfb2_kernel<M, R1, R2, NB, TT, NT, MINB>;
     SDRGPU_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::smem_bytes));
     const int grid = (p.n_blocks + NB - 1) / NB;
     kernel<<<grid, NT, L::smem_bytes, h->stream>>>(p);
@@ -793,6 +831,8 @@ sdrgpu_status sdrgpu_chan_process(sdrgpu_channelizer *h, const float *iq, int n_
         p.n_sel = h->n_sel;
         p.layout = layout;
         p.gain_exact = h->gain_exact;
+        p.identity = h->identity;
+        p.gain_uniform = h->gain_uniform;
         p.inv_m = 1.0f / (float)h->M;
         p.n_factors = (int)h->factors.size();
         for (int i = 0; i < p.n_factors; i++) {
@@ -802,9 +842,12 @@ sdrgpu_status sdrgpu_chan_process(sdrgpu_channelizer *h, const float *iq, int n_
         const int grid = (n_blocks + h->NB - 1) / h->NB;
         h->timer.begin(h->stream);
         sdrgpu_status st;
-        if (h->fast_r1 && h->M == 400) st = launch_pfb2<400, 20, 20, 16, 9, 320>(h, p);
-        else if (h->fast_r1 && h->M == 800) st = launch_pfb2<800, 32, 25, 8, 9, 256>(h, p);
-        else if (h->fast_r1 && h->M == 96) st = launch_pfb2<96, 8, 12, 16, 9, 192>(h, p);
+        // tile sizes measured on B200 (profiles/): M = 400 runs best as 8-block tiles, 200 threads, 4 CTAs per SM
+        static const int variant = getenv("SDRGPU_PFB_VARIANT") ? atoi(getenv("SDRGPU_PFB_VARIANT")) : 0;
+        if (h->fast_r1 && h->M == 400 && variant == 1) st = launch_pfb2<400, 20, 20, 16, 9, 320, 2>(h, p);
+        else if (h->fast_r1 && h->M == 400) st = launch_pfb2<400, 20, 20, 8, 9, 200, 4>(h, p);
+        else if (h->fast_r1 && h->M == 800) st = launch_pfb2<800, 32, 25, 8, 9, 256, 2>(h, p);
+        else if (h->fast_r1 && h->M == 96) st = launch_pfb2<96, 8, 12, 16, 9, 192, 2>(h, p);
         else if (h->NB == 16) st = (h->T == 9) ? launch_pfb<16, 9>(h, p, grid) : launch_pfb<16, 0>(h, p, grid);
         else st = (h->T == 9) ? launch_pfb<8, 9>(h, p, grid) : launch_pfb<8, 0>(h, p, grid);
         h->timer.end(h->stream);
