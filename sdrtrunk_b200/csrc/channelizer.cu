@@ -36,6 +36,7 @@ namespace {
 
 constexpr int kMaxFactors = 16;
 constexpr int kThreads = 256;
+constexpr int kMaxEvents = 64;
 
 struct ChanParams {
     const float2 *state;  // [state_len] history ((2T-1)*M/2 samples) followed by the leftover samples
@@ -479,6 +480,16 @@ struct sdrgpu_channelizer {
     int max_in_complex = 0, max_blocks = 0;
     int leftover = 0, parity0 = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;   // H2D / D2H streams of the chunked host path
+    cudaEvent_t events[kMaxEvents] = {};
+    sdrgpu_status ensure_copy_streams()
+    {
+        if (copy_in) return SDRGPU_OK;
+        SDRGPU_CUDA(cudaStreamCreateWithFlags(&copy_in, cudaStreamNonBlocking));
+        SDRGPU_CUDA(cudaStreamCreateWithFlags(&copy_out, cudaStreamNonBlocking));
+        for (auto &e : events) SDRGPU_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        return SDRGPU_OK;
+    }
     float *d_taps = nullptr;
     float2 *d_tw = nullptr;
     float2 *d_tw2 = nullptr;   // pfb2_kernel inter-step twiddles
@@ -565,6 +576,88 @@ sdrgpu_status launch_pfb(const sdrgpu_channelizer *h, const ChanParams &p, int g
 }  // namespace
 
 int sdrgpu::chan_selected_count(const sdrgpu_channelizer *h) { return h ? h->n_sel : 0; }
+
+// Enqueues the channelizer kernels for n_in device-resident complex samples on the handle's stream and updates the
+// host-side framing state (leftover samples, block parity, history ping-pong).  No copies, no synchronisation.
+sdrgpu_status sdrgpu::chan_enqueue(sdrgpu_channelizer *h, const float2 *d_in, int n_in, float *d_out, long long stride,
+                                   int layout, int *n_blocks_out)
+{
+    const int total = h->leftover + n_in;
+    const int n_blocks = total / h->half;
+    if (n_blocks_out) *n_blocks_out = n_blocks;
+    const float2 *state = h->d_state[h->cur_state];
+    const int state_len = h->H + h->leftover;
+    if (n_blocks > 0) {
+        ChanParams p{};
+        p.state = state;
+        p.in = d_in;
+        p.taps = h->d_taps;
+        p.tw = h->d_tw;
+        p.tw2 = h->d_tw2;
+        p.out = d_out;
+        p.sel = h->d_sel;
+        p.gain_f = h->d_gain_f;
+        p.gain_d = h->d_gain_d;
+        p.out_stride = stride;
+        p.state_len = state_len;
+        p.n_in = n_in;
+        p.M = h->M;
+        p.T = h->T;
+        p.half = h->half;
+        p.H = h->H;
+        p.n_blocks = n_blocks;
+        p.parity0 = h->parity0;
+        p.n_sel = h->n_sel;
+        p.layout = layout;
+        p.gain_exact = h->gain_exact;
+        p.identity = h->identity;
+        p.gain_uniform = h->gain_uniform;
+        p.inv_m = 1.0f / (float)h->M;
+        p.n_factors = (int)h->factors.size();
+        for (int i = 0; i < p.n_factors; i++) {
+            p.factors[i] = h->factors[i];
+            p.magic_s[i] = h->magic[i];
+        }
+        const int grid = (n_blocks + h->NB - 1) / h->NB;
+        h->timer.begin(h->stream);
+        sdrgpu_status st;
+        // tile sizes measured on B200 (profiles/): M = 400 runs best as 8-block tiles, 200 threads, 4 CTAs per SM
+        static const int variant = getenv("SDRGPU_PFB_VARIANT") ? atoi(getenv("SDRGPU_PFB_VARIANT")) : 0;
+        if (h->fast_r1 && h->M == 400 && variant == 1) st = launch_pfb2<400, 20, 20, 16, 9, 320, 2>(h, p);
+        else if (h->fast_r1 && h->M == 400) st = launch_pfb2<400, 20, 20, 8, 9, 200, 4>(h, p);
+        else if (h->fast_r1 && h->M == 800) st = launch_pfb2<800, 32, 25, 8, 9, 256, 2>(h, p);
+        else if (h->fast_r1 && h->M == 96) st = launch_pfb2<96, 8, 12, 16, 9, 192, 2>(h, p);
+        else if (h->NB == 16) st = (h->T == 9) ? launch_pfb<16, 9>(h, p, grid) : launch_pfb<16, 0>(h, p, grid);
+        else st = (h->T == 9) ? launch_pfb<8, 9>(h, p, grid) : launch_pfb<8, 0>(h, p, grid);
+        h->timer.end(h->stream);
+        SDRGPU_TRY(st);
+    }
+    // carry the history + leftover over to the next call
+    const int consumed = n_blocks * h->half;
+    const int new_leftover = total - consumed;
+    const int new_len = h->H + new_leftover;
+    float2 *next = h->d_state[h->cur_state ^ 1];
+    if (n_in > 0) {
+        int grid = (new_len + 255) / 256;
+        if (grid > 1024) grid = 1024;
+        save_state_kernel<<<grid, 256, 0, h->stream>>>(state, state_len, d_in, n_in, consumed, next, new_len);
+        count_launch();
+        SDRGPU_CUDA(cudaGetLastError());
+        h->cur_state ^= 1;
+    }
+    h->leftover = new_leftover;
+    h->parity0 = (h->parity0 + n_blocks) & 1;
+    return SDRGPU_OK;
+}
+
+cudaStream_t sdrgpu::chan_stream(const sdrgpu_channelizer *h) { return h->stream; }
+float2 *sdrgpu::chan_staging_in(sdrgpu_channelizer *h)
+{
+    if (!h->d_in && cudaMalloc(&h->d_in, sizeof(float2) * (size_t)h->max_in_complex) != cudaSuccess) return nullptr;
+    return h->d_in;
+}
+int sdrgpu::chan_half(const sdrgpu_channelizer *h) { return h->half; }
+
 
 extern "C" {
 
@@ -691,6 +784,10 @@ sdrgpu_status sdrgpu_chan_destroy(sdrgpu_channelizer *h)
     cudaFree(h->d_gain_f);
     cudaFree(h->d_gain_d);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    if (h->copy_in) cudaStreamDestroy(h->copy_in);
+    if (h->copy_out) cudaStreamDestroy(h->copy_out);
+    for (auto &e : h->events)
+        if (e) cudaEventDestroy(e);
     delete h;
     return SDRGPU_OK;
 }
@@ -775,112 +872,78 @@ sdrgpu_status sdrgpu_chan_process(sdrgpu_channelizer *h, const float *iq, int n_
             return fail(SDRGPU_ERR_INVALID_ARG, "device output must be 8-byte aligned");
     }
 
-    const float2 *d_in = nullptr;
-    if (n_in > 0) {
-        if (in_mem == SDRGPU_HOST) {
-            if (!h->d_in) SDRGPU_CUDA(cudaMalloc(&h->d_in, sizeof(float2) * (size_t)h->max_in_complex));
-            SDRGPU_CUDA(cudaMemcpyAsync(h->d_in, iq, sizeof(float) * (size_t)n_floats, cudaMemcpyHostToDevice, h->stream));
-            d_in = h->d_in;
-        } else {
-            d_in = reinterpret_cast<const float2 *>(iq);
+    // device staging for host buffers
+    float *d_out = out;
+    long long stride = out_stride_floats;
+    if (out_mem == SDRGPU_HOST && n_blocks > 0) {
+        const size_t need = (layout == SDRGPU_LAYOUT_CHANNELS) ? sizeof(float) * 2 * (size_t)n_blocks * (size_t)rows
+                                                              : sizeof(float) * 2 * (size_t)n_blocks * (size_t)h->M;
+        if (need > h->d_out_bytes) {
+            if (h->d_out) {
+                SDRGPU_CUDA(cudaStreamSynchronize(h->stream));
+                cudaFree(h->d_out);
+                h->d_out = nullptr;
+            }
+            const size_t cap = sizeof(float) * 2 * (size_t)h->max_blocks * (size_t)(h->M > h->n_sel ? h->M : h->n_sel);
+            const size_t bytes = need > cap ? need : cap;
+            SDRGPU_CUDA(cudaMalloc(&h->d_out, bytes));
+            h->d_out_bytes = bytes;
         }
+        d_out = h->d_out;
+        stride = 2LL * n_blocks;
+    }
+    if (in_mem == SDRGPU_HOST && n_in > 0 && !h->d_in)
+        SDRGPU_CUDA(cudaMalloc(&h->d_in, sizeof(float2) * (size_t)h->max_in_complex));
+
+    if (in_mem == SDRGPU_DEVICE && out_mem == SDRGPU_DEVICE) {
+        int got = 0;
+        return sdrgpu::chan_enqueue(h, reinterpret_cast<const float2 *>(iq), n_in, out, out_stride_floats, layout, &got);
     }
 
-    const float2 *state = h->d_state[h->cur_state];
-    const int state_len = h->H + h->leftover;
-
-    if (n_blocks > 0) {
-        float *d_out = out;
-        long long stride = out_stride_floats;
-        if (out_mem == SDRGPU_HOST) {
-            const size_t need = (layout == SDRGPU_LAYOUT_CHANNELS) ? sizeof(float) * 2 * (size_t)n_blocks * (size_t)rows
-                                                                  : sizeof(float) * 2 * (size_t)n_blocks * (size_t)h->M;
-            if (need > h->d_out_bytes) {
-                if (h->d_out) {
-                    SDRGPU_CUDA(cudaStreamSynchronize(h->stream));
-                    cudaFree(h->d_out);
-                    h->d_out = nullptr;
-                }
-                const size_t cap = sizeof(float) * 2 * (size_t)h->max_blocks * (size_t)(h->M > h->n_sel ? h->M : h->n_sel);
-                const size_t bytes = need > cap ? need : cap;
-                SDRGPU_CUDA(cudaMalloc(&h->d_out, bytes));
-                h->d_out_bytes = bytes;
-            }
-            d_out = h->d_out;
-            stride = 2LL * n_blocks;
+    // Host buffers: the call is cut into chunks so that the H2D copy of chunk i+1, the kernels of chunk i and the D2H
+    // copy of chunk i-1 overlap on three streams (PCIe is full duplex; the copies, not the kernels, bound this path).
+    // Block framing carries over between chunks exactly as between calls, so the result does not depend on the cut.
+    SDRGPU_TRY(h->ensure_copy_streams());
+    const int tile = h->half * 64;                                    // whole tiles of the kernels
+    int chunk = (n_in + 7) / 8;
+    chunk = (chunk + tile - 1) / tile * tile;
+    if (chunk < tile) chunk = tile;
+    int done_in = 0, done_blocks = 0, ci = 0;
+    while (done_in < n_in || (n_in == 0 && ci == 0)) {
+        const int n = (n_in - done_in < chunk) ? n_in - done_in : chunk;
+        const float2 *src_dev = reinterpret_cast<const float2 *>(iq) + done_in;
+        cudaEvent_t ev_in = h->events[(2 * ci) % kMaxEvents], ev_k = h->events[(2 * ci + 1) % kMaxEvents];
+        if (in_mem == SDRGPU_HOST && n > 0) {
+            SDRGPU_CUDA(cudaMemcpyAsync(h->d_in + done_in, iq + 2 * (size_t)done_in, sizeof(float2) * (size_t)n,
+                                        cudaMemcpyHostToDevice, h->copy_in));
+            SDRGPU_CUDA(cudaEventRecord(ev_in, h->copy_in));
+            SDRGPU_CUDA(cudaStreamWaitEvent(h->stream, ev_in, 0));
+            src_dev = h->d_in + done_in;
         }
-        ChanParams p{};
-        p.state = state;
-        p.in = d_in;
-        p.taps = h->d_taps;
-        p.tw = h->d_tw;
-        p.tw2 = h->d_tw2;
-        p.out = d_out;
-        p.sel = h->d_sel;
-        p.gain_f = h->d_gain_f;
-        p.gain_d = h->d_gain_d;
-        p.out_stride = stride;
-        p.state_len = state_len;
-        p.n_in = n_in;
-        p.M = h->M;
-        p.T = h->T;
-        p.half = h->half;
-        p.H = h->H;
-        p.n_blocks = n_blocks;
-        p.parity0 = h->parity0;
-        p.n_sel = h->n_sel;
-        p.layout = layout;
-        p.gain_exact = h->gain_exact;
-        p.identity = h->identity;
-        p.gain_uniform = h->gain_uniform;
-        p.inv_m = 1.0f / (float)h->M;
-        p.n_factors = (int)h->factors.size();
-        for (int i = 0; i < p.n_factors; i++) {
-            p.factors[i] = h->factors[i];
-            p.magic_s[i] = h->magic[i];
-        }
-        const int grid = (n_blocks + h->NB - 1) / h->NB;
-        h->timer.begin(h->stream);
-        sdrgpu_status st;
-        // tile sizes measured on B200 (profiles/): M = 400 runs best as 8-block tiles, 200 threads, 4 CTAs per SM
-        static const int variant = getenv("SDRGPU_PFB_VARIANT") ? atoi(getenv("SDRGPU_PFB_VARIANT")) : 0;
-        if (h->fast_r1 && h->M == 400 && variant == 1) st = launch_pfb2<400, 20, 20, 16, 9, 320, 2>(h, p);
-        else if (h->fast_r1 && h->M == 400) st = launch_pfb2<400, 20, 20, 8, 9, 200, 4>(h, p);
-        else if (h->fast_r1 && h->M == 800) st = launch_pfb2<800, 32, 25, 8, 9, 256, 2>(h, p);
-        else if (h->fast_r1 && h->M == 96) st = launch_pfb2<96, 8, 12, 16, 9, 192, 2>(h, p);
-        else if (h->NB == 16) st = (h->T == 9) ? launch_pfb<16, 9>(h, p, grid) : launch_pfb<16, 0>(h, p, grid);
-        else st = (h->T == 9) ? launch_pfb<8, 9>(h, p, grid) : launch_pfb<8, 0>(h, p, grid);
-        h->timer.end(h->stream);
-        SDRGPU_TRY(st);
-        if (out_mem == SDRGPU_HOST) {
+        float *dst = nullptr;
+        if (n_blocks > 0)
+            dst = (layout == SDRGPU_LAYOUT_CHANNELS) ? d_out + 2 * (size_t)done_blocks : d_out + 2 * (size_t)done_blocks * h->M;
+        int got = 0;
+        SDRGPU_TRY(sdrgpu::chan_enqueue(h, src_dev, n, dst, stride, layout, &got));
+        if (out_mem == SDRGPU_HOST && got > 0) {
+            SDRGPU_CUDA(cudaEventRecord(ev_k, h->stream));
+            SDRGPU_CUDA(cudaStreamWaitEvent(h->copy_out, ev_k, 0));
             if (layout == SDRGPU_LAYOUT_CHANNELS) {
-                SDRGPU_CUDA(cudaMemcpy2DAsync(out, sizeof(float) * (size_t)out_stride_floats, d_out,
-                                              sizeof(float) * (size_t)stride, sizeof(float) * 2 * (size_t)n_blocks,
-                                              (size_t)rows, cudaMemcpyDeviceToHost, h->stream));
+                SDRGPU_CUDA(cudaMemcpy2DAsync(out + 2 * (size_t)done_blocks, sizeof(float) * (size_t)out_stride_floats, dst,
+                                              sizeof(float) * (size_t)stride, sizeof(float) * 2 * (size_t)got, (size_t)rows,
+                                              cudaMemcpyDeviceToHost, h->copy_out));
             } else {
-                SDRGPU_CUDA(cudaMemcpyAsync(out, d_out, sizeof(float) * 2 * (size_t)n_blocks * (size_t)h->M,
-                                            cudaMemcpyDeviceToHost, h->stream));
+                SDRGPU_CUDA(cudaMemcpyAsync(out + 2 * (size_t)done_blocks * h->M, dst, sizeof(float) * 2 * (size_t)got * (size_t)h->M,
+                                            cudaMemcpyDeviceToHost, h->copy_out));
             }
         }
+        done_in += n;
+        done_blocks += got;
+        ci++;
+        if (n_in == 0) break;
     }
-
-    // carry the history + leftover over to the next call
-    const int consumed = n_blocks * h->half;
-    const int new_leftover = total - consumed;
-    const int new_len = h->H + new_leftover;
-    float2 *next = h->d_state[h->cur_state ^ 1];
-    if (n_in > 0) {
-        int grid = (new_len + 255) / 256;
-        if (grid > 1024) grid = 1024;
-        save_state_kernel<<<grid, 256, 0, h->stream>>>(state, state_len, d_in, n_in, consumed, next, new_len);
-        count_launch();
-        SDRGPU_CUDA(cudaGetLastError());
-        h->cur_state ^= 1;
-    }
-    h->leftover = new_leftover;
-    h->parity0 = (h->parity0 + n_blocks) & 1;
-
-    if (out_mem == SDRGPU_HOST || in_mem == SDRGPU_HOST) SDRGPU_CUDA(cudaStreamSynchronize(h->stream));
+    SDRGPU_CUDA(cudaStreamSynchronize(h->stream));
+    if (out_mem == SDRGPU_HOST) SDRGPU_CUDA(cudaStreamSynchronize(h->copy_out));
     return SDRGPU_OK;
 }
 

@@ -41,6 +41,12 @@ inline sdrgpu_status fail(sdrgpu_status code, const char *fmt, ...)
 
 // number of output rows the channelizer currently selects (channelizer.cu)
 int chan_selected_count(const sdrgpu_channelizer *h);
+// channelizer internals the fused pipeline (bank.cu) drives directly
+sdrgpu_status chan_enqueue(sdrgpu_channelizer *h, const float2 *d_in, int n_in, float *d_out, long long stride, int layout,
+                           int *n_blocks_out);
+cudaStream_t chan_stream(const sdrgpu_channelizer *h);
+float2 *chan_staging_in(sdrgpu_channelizer *h);
+int chan_half(const sdrgpu_channelizer *h);
 
 inline void count_launch(int n = 1) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 
