@@ -95,6 +95,10 @@ sdrgpu_status sdrgpu_chan_destroy(sdrgpu_channelizer *h);
 sdrgpu_status sdrgpu_chan_set_stream(sdrgpu_channelizer *h, void *cuda_stream);
 sdrgpu_status sdrgpu_chan_sync(sdrgpu_channelizer *h);
 
+/* tuner sample rate in Hz (the sampleRate argument of the ComplexPolyphaseChannelizerM2 constructors / setRates,
+ * :93,114,169): needed before two-bin or frequency-corrected channels are selected (channel rate = 2 * rate / M) */
+sdrgpu_status sdrgpu_chan_set_sample_rate(sdrgpu_channelizer *h, double sample_rate);
+
 /* One output channel of the channel layout: one polyphase bin (bin2 < 0; OneChannelOutputProcessor) or two
  * adjacent bins recombined (TwoChannelOutputProcessor); frequency_offset_hz drives the frequency-correction
  * oscillator (ChannelOutputProcessor.setFrequencyOffset, :91-95); gain as PolyphaseChannelManager passes it
@@ -107,7 +111,10 @@ typedef struct {
 } sdrgpu_output_channel;
 
 /* select the output channels (default after create: every bin 0..M-1 as a one-bin channel with gain M and no
- * offset).  synthesis_filter (may be NULL if no two-bin channel) = getSincM2Synthesizer taps. */
+ * offset).  synthesis_filter (may be NULL if no two-bin channel) = getSincM2Synthesizer taps.  Two-bin channels run
+ * TwoChannelSynthesizerM2 + FS4DownConverter + the frequency-correction Oscillator (always, as
+ * TwoChannelOutputProcessor.java:113 does); one-bin channels run the Oscillator only with a non-zero offset
+ * (OneChannelOutputProcessor.java:92-95).  Selecting resets the oscillators and synthesizer histories. */
 sdrgpu_status sdrgpu_chan_select(sdrgpu_channelizer *h, const sdrgpu_output_channel *channels, int n_channels,
                                  const float *synthesis_filter, int n_synthesis_taps);
 

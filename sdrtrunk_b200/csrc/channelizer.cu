@@ -25,6 +25,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "common.cuh"
@@ -49,6 +50,9 @@ struct ChanParams {
     const float *gain_f;  // [n_sel] float gain (used when gain_exact)
     const double *gain_d; // [n_sel]
     long long out_stride; // floats per output row (channel layout)
+    float *out2;          // rows >= n_main (second bins of two-bin channels) go here
+    long long out2_stride;
+    int n_main;
     int state_len, n_in;
     int M, T, half, H;
     int n_blocks, parity0;
@@ -243,7 +247,8 @@ __global__ void __launch_bounds__(kThreads) pfb_ifft_kernel(const ChanParams p)
                 v.x = __double2float_rn(__dmul_rn((double)v.x, g));
                 v.y = __double2float_rn(__dmul_rn((double)v.y, g));
             }
-            *reinterpret_cast<float2 *>(p.out + (size_t)c * p.out_stride + 2 * (size_t)b) = v;
+            float *row = c < p.n_main ? p.out + (size_t)c * p.out_stride : p.out2 + (size_t)(c - p.n_main) * p.out2_stride;
+            *reinterpret_cast<float2 *>(row + 2 * (size_t)b) = v;
         }
     } else {
         const int total = M * NB;
@@ -432,7 +437,8 @@ __global__ void __launch_bounds__(NT, MINB) pfb2_kernel(const ChanParams p)
                     float2 v = X[__ldg(p.sel + c) * LDX + bl];
                     v.x = __fmul_rn(__fmul_rn(v.x, inv_m), g);
                     v.y = __fmul_rn(__fmul_rn(v.y, inv_m), g);
-                    *reinterpret_cast<float2 *>(out + (size_t)c * p.out_stride) = v;
+                    float *row = c < p.n_main ? p.out + (size_t)c * p.out_stride : p.out2 + (size_t)(c - p.n_main) * p.out2_stride;
+                    *reinterpret_cast<float2 *>(row + 2 * (size_t)b) = v;
                 }
             } else {
                 for (int c = row0; c < p.n_sel; c += ROWS) {
@@ -440,7 +446,8 @@ __global__ void __launch_bounds__(NT, MINB) pfb2_kernel(const ChanParams p)
                     float2 v = X[__ldg(p.sel + c) * LDX + bl];
                     v.x = __double2float_rn(__dmul_rn((double)__fmul_rn(v.x, inv_m), g));
                     v.y = __double2float_rn(__dmul_rn((double)__fmul_rn(v.y, inv_m), g));
-                    *reinterpret_cast<float2 *>(out + (size_t)c * p.out_stride) = v;
+                    float *row = c < p.n_main ? p.out + (size_t)c * p.out_stride : p.out2 + (size_t)(c - p.n_main) * p.out2_stride;
+                    *reinterpret_cast<float2 *>(row + 2 * (size_t)b) = v;
                 }
             }
         }
@@ -456,6 +463,124 @@ __global__ void __launch_bounds__(NT, MINB) pfb2_kernel(const ChanParams p)
             *reinterpret_cast<float2 *>(p.out + ((size_t)b * M + k) * 2) = v;
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Post-processing of the "special" output channels, in place on their rows, one warp per channel:
+//   two-bin channels  TwoChannelOutputProcessor.process + TwoChannelSynthesizerM2.process + FS4DownConverter
+//                     (J/dsp/filter/channelizer/output/TwoChannelOutputProcessor.java:98-121,
+//                      J/dsp/filter/channelizer/TwoChannelSynthesizerM2.java:90-158, J/dsp/mixer/FS4DownConverter.java:32-68)
+//   frequency offset  Oscillator mix (J/dsp/mixer/Oscillator.java:42-68, AbstractOscillator.java:102-116): the rotator
+//                     is a float recursion with fastNormalize, so it runs as a sequential chain that every lane
+//                     walks, lane i keeping the value of sample i
+//   gain              ReusableComplexBuffer.applyGain: samples[x] = (float)(samples[x] * (double) gain)
+// The pfb kernels leave these rows at gain 1 (bin values after the 1/M of the inverse FFT).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kMaxSynthEntries = 32;   // serpentine entries (4 floats each): filter.length / 2
+
+struct PostChannel {
+    int row, row2;          // output row; scratch row of the second bin (-1 for one-bin channels)
+    int mix;                // oscillator enabled
+    float angle_i, angle_q; // Oscillator: Complex.fromAngle((float)(2 pi f / fs))
+    double gain;
+};
+
+struct PostState {
+    float cur_i, cur_q;     // Oscillator current vector, starts at (0, -1)
+    int top_block, fs4;
+    float4 hist[kMaxSynthEntries];  // the newest serpentine entries, oldest first
+};
+
+struct SynthFilter {
+    float f[4 * kMaxSynthEntries];  // taps duplicated for I and Q (TwoChannelSynthesizerM2.init)
+    int entries;                     // len / 4
+};
+
+__global__ void __launch_bounds__(32) post_channel_kernel(float *out, long long out_stride, const float *out2,
+                                                          long long out2_stride, int n, const PostChannel *chans,
+                                                          PostState *states, const __grid_constant__ SynthFilter filt)
+{
+    __shared__ float4 ent[kMaxSynthEntries + 32];
+    const int lane = threadIdx.x;
+    const PostChannel c = chans[blockIdx.x];
+    PostState *st = states + blockIdx.x;
+    float2 *row = reinterpret_cast<float2 *>(out + (size_t)c.row * out_stride);
+    const float2 *row2 = c.row2 >= 0 ? reinterpret_cast<const float2 *>(out2 + (size_t)c.row2 * out2_stride) : nullptr;
+    const int H = filt.entries - 1;   // history entries a sample needs besides its own
+    float cur_i = st->cur_i, cur_q = st->cur_q;
+    const int top0 = st->top_block, fs40 = st->fs4;
+    if (row2)
+        for (int i = lane; i < H; i += 32) ent[i] = st->hist[i];
+    __syncwarp();
+    for (int base = 0; base < n; base += 32) {
+        const int k = base + lane;
+        const bool valid = k < n;
+        float2 v = valid ? row[k] : make_float2(0.f, 0.f);
+        if (row2) {
+            const float2 b = valid ? row2[k] : make_float2(0.f, 0.f);
+            // FloatFFT_1D(2).complexInverse(buffer, true): butterfly, then * 1/2
+            const float i0 = __fmul_rn(__fadd_rn(v.x, b.x), 0.5f), i1 = __fmul_rn(__fadd_rn(v.y, b.y), 0.5f);
+            const float i2 = __fmul_rn(__fsub_rn(v.x, b.x), 0.5f), i3 = __fmul_rn(__fsub_rn(v.y, b.y), 0.5f);
+            const bool top = ((top0 ^ k) & 1) != 0;   // mTopBlockIndicator toggles per sample
+            ent[H + lane] = top ? make_float4(i0, i1, i2, i3) : make_float4(i2, i3, i0, i1);
+            __syncwarp();
+            // product[y] = serpentine[y] * filter[y]; accumulators sum the I / Q lanes in index order
+            float acc_i = 0.0f, acc_q = 0.0f;
+            for (int j = 0; j < filt.entries; j++) {
+                const float4 e = ent[H + lane - j];
+                const float p0 = __fmul_rn(e.x, filt.f[4 * j]), p1 = __fmul_rn(e.y, filt.f[4 * j + 1]);
+                const float p2 = __fmul_rn(e.z, filt.f[4 * j + 2]), p3 = __fmul_rn(e.w, filt.f[4 * j + 3]);
+                acc_i = __fadd_rn(__fadd_rn(acc_i, p0), p2);
+                acc_q = __fadd_rn(__fadd_rn(acc_q, p1), p3);
+            }
+            // FS4DownConverter: multiply by (-j)^pointer
+            switch ((fs40 + k) & 3) {
+                case 1: v = make_float2(acc_q, -acc_i); break;
+                case 2: v = make_float2(-acc_i, -acc_q); break;
+                case 3: v = make_float2(-acc_q, acc_i); break;
+                default: v = make_float2(acc_i, acc_q); break;
+            }
+            __syncwarp();
+            // keep the newest H entries for the next 32 samples
+            const int count = min(32, n - base);
+            float4 keep = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (lane < H) keep = ent[count + lane];
+            __syncwarp();
+            if (lane < H) ent[lane] = keep;
+            __syncwarp();
+        }
+        if (c.mix) {
+            // AbstractOscillator.mixComplex: sample * current, then rotate(): current *= angle, fastNormalize
+            float my_i = cur_i, my_q = cur_q;
+            const int count = min(32, n - base);
+            for (int i = 0; i < count; i++) {
+                if (i == lane) {
+                    my_i = cur_i;
+                    my_q = cur_q;
+                }
+                const float ni = __fsub_rn(__fmul_rn(cur_i, c.angle_i), __fmul_rn(cur_q, c.angle_q));
+                const float nq = __fadd_rn(__fmul_rn(cur_q, c.angle_i), __fmul_rn(cur_i, c.angle_q));
+                const float norm = __fadd_rn(__fmul_rn(ni, ni), __fmul_rn(nq, nq));
+                const float scalor = __fsub_rn(1.9999f, norm);
+                cur_i = __fmul_rn(ni, scalor);
+                cur_q = __fmul_rn(nq, scalor);
+            }
+            const float mi = __fsub_rn(__fmul_rn(v.x, my_i), __fmul_rn(v.y, my_q));
+            const float mq = __fadd_rn(__fmul_rn(v.y, my_i), __fmul_rn(v.x, my_q));
+            v = make_float2(mi, mq);
+        }
+        v.x = __double2float_rn(__dmul_rn((double)v.x, c.gain));
+        v.y = __double2float_rn(__dmul_rn((double)v.y, c.gain));
+        if (valid) row[k] = v;
+    }
+    if (lane == 0) {
+        st->cur_i = cur_i;
+        st->cur_q = cur_q;
+        st->top_block = (top0 ^ n) & 1;
+        st->fs4 = (fs40 + n) & 3;
+    }
+    if (row2)
+        for (int i = lane; i < H; i += 32) st->hist[i] = ent[i];
 }
 
 // new_state[i] = S[consumed + i], S = [state | in]
@@ -503,6 +628,13 @@ struct sdrgpu_channelizer {
     int *d_sel = nullptr;
     float *d_gain_f = nullptr;
     double *d_gain_d = nullptr;
+    double sample_rate = 0.0;          // tuner sample rate (Hz); needed for frequency-corrected channels
+    int n_rows = 0;                    // rows the pfb kernel writes: n_sel output rows + scratch rows of second bins
+    int n_post = 0;                    // special channels (two-bin and / or frequency offset)
+    PostChannel *d_post = nullptr;
+    PostState *d_post_state = nullptr;
+    float *d_out2 = nullptr;           // scratch rows [n_rows - n_sel][2 * max_blocks]
+    SynthFilter synth{};
     int gain_exact = 1;
     int identity = 0;
     float gain_uniform = 0.0f;
@@ -518,31 +650,78 @@ namespace {
 sdrgpu_status upload_selection(sdrgpu_channelizer *h)
 {
     const int n = (int)h->channels.size();
-    std::vector<int> sel(n);
-    std::vector<float> gf(n);
-    std::vector<double> gd(n);
-    int exact = 1;
+    std::vector<int> sel;
+    std::vector<float> gf;
+    std::vector<double> gd;
+    std::vector<PostChannel> post;
+    int exact = 1, n_two = 0;
     for (int i = 0; i < n; i++) {
-        sel[i] = h->channels[i].bin1;
-        gd[i] = h->channels[i].gain;
-        gf[i] = (float)gd[i];
-        if ((double)gf[i] != gd[i]) exact = 0;
+        const sdrgpu_output_channel &c = h->channels[i];
+        const bool special = c.bin2 >= 0 || c.frequency_offset_hz != 0;
+        sel.push_back(c.bin1);
+        // special rows leave the pfb kernel at gain 1; post_channel_kernel applies the gain after mixing
+        gd.push_back(special ? 1.0 : c.gain);
+        gf.push_back((float)gd.back());
+        if ((double)gf.back() != gd.back()) exact = 0;
+        if (special) {
+            PostChannel pc{};
+            pc.row = i;
+            pc.row2 = c.bin2 >= 0 ? n_two++ : -1;
+            // TwoChannelOutputProcessor mixes unconditionally, OneChannelOutputProcessor only with an offset
+            pc.mix = 1;
+            // Oscillator.update: anglePerSample = (float)(2 pi f / fs); Complex.fromAngle(float) -> (float)cos, (float)sin
+            const double channel_rate = 2.0 * h->sample_rate / (double)h->M;
+            const float angle = (float)(2.0 * 3.14159265358979323846 * (double)c.frequency_offset_hz / channel_rate);
+            pc.angle_i = (float)cos((double)angle);
+            pc.angle_q = (float)sin((double)angle);
+            pc.gain = c.gain;
+            post.push_back(pc);
+        }
     }
-    if (h->d_sel) cudaFree(h->d_sel);
-    if (h->d_gain_f) cudaFree(h->d_gain_f);
-    if (h->d_gain_d) cudaFree(h->d_gain_d);
+    for (int i = 0; i < n; i++)
+        if (h->channels[i].bin2 >= 0) {   // scratch rows: the second bins, gain 1
+            sel.push_back(h->channels[i].bin2);
+            gd.push_back(1.0);
+            gf.push_back(1.0f);
+        }
+    const int rows = (int)sel.size();
+    cudaFree(h->d_sel);
+    cudaFree(h->d_gain_f);
+    cudaFree(h->d_gain_d);
+    cudaFree(h->d_post);
+    cudaFree(h->d_post_state);
+    cudaFree(h->d_out2);
     h->d_sel = nullptr;
     h->d_gain_f = nullptr;
     h->d_gain_d = nullptr;
-    SDRGPU_CUDA(cudaMalloc(&h->d_sel, sizeof(int) * (size_t)n));
-    SDRGPU_CUDA(cudaMalloc(&h->d_gain_f, sizeof(float) * (size_t)n));
-    SDRGPU_CUDA(cudaMalloc(&h->d_gain_d, sizeof(double) * (size_t)n));
-    SDRGPU_CUDA(cudaMemcpy(h->d_sel, sel.data(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice));
-    SDRGPU_CUDA(cudaMemcpy(h->d_gain_f, gf.data(), sizeof(float) * (size_t)n, cudaMemcpyHostToDevice));
-    SDRGPU_CUDA(cudaMemcpy(h->d_gain_d, gd.data(), sizeof(double) * (size_t)n, cudaMemcpyHostToDevice));
+    h->d_post = nullptr;
+    h->d_post_state = nullptr;
+    h->d_out2 = nullptr;
+    SDRGPU_CUDA(cudaMalloc(&h->d_sel, sizeof(int) * (size_t)rows));
+    SDRGPU_CUDA(cudaMalloc(&h->d_gain_f, sizeof(float) * (size_t)rows));
+    SDRGPU_CUDA(cudaMalloc(&h->d_gain_d, sizeof(double) * (size_t)rows));
+    SDRGPU_CUDA(cudaMemcpy(h->d_sel, sel.data(), sizeof(int) * (size_t)rows, cudaMemcpyHostToDevice));
+    SDRGPU_CUDA(cudaMemcpy(h->d_gain_f, gf.data(), sizeof(float) * (size_t)rows, cudaMemcpyHostToDevice));
+    SDRGPU_CUDA(cudaMemcpy(h->d_gain_d, gd.data(), sizeof(double) * (size_t)rows, cudaMemcpyHostToDevice));
+    if (!post.empty()) {
+        std::vector<PostState> init(post.size());
+        std::memset(init.data(), 0, sizeof(PostState) * init.size());
+        for (auto &st : init) {
+            st.cur_i = 0.0f;   // Oscillator.java:24: mCurrentAngle = new Complex(0.0f, -1.0f)
+            st.cur_q = -1.0f;
+            st.top_block = 1;  // TwoChannelSynthesizerM2: mTopBlockIndicator = true
+        }
+        SDRGPU_CUDA(cudaMalloc(&h->d_post, sizeof(PostChannel) * post.size()));
+        SDRGPU_CUDA(cudaMalloc(&h->d_post_state, sizeof(PostState) * post.size()));
+        SDRGPU_CUDA(cudaMemcpy(h->d_post, post.data(), sizeof(PostChannel) * post.size(), cudaMemcpyHostToDevice));
+        SDRGPU_CUDA(cudaMemcpy(h->d_post_state, init.data(), sizeof(PostState) * init.size(), cudaMemcpyHostToDevice));
+    }
+    if (n_two > 0) SDRGPU_CUDA(cudaMalloc(&h->d_out2, sizeof(float) * 2 * (size_t)h->max_blocks * (size_t)n_two));
     h->n_sel = n;
+    h->n_rows = rows;
+    h->n_post = (int)post.size();
     h->gain_exact = exact;
-    h->identity = exact && n == h->M;
+    h->identity = exact && n == h->M && post.empty();
     for (int i = 0; i < n && h->identity; i++)
         if (sel[i] != i || gf[i] != gf[0]) h->identity = 0;
     h->gain_uniform = n > 0 ? gf[0] : 0.0f;
@@ -599,6 +778,9 @@ sdrgpu_status sdrgpu::chan_enqueue(sdrgpu_channelizer *h, const float2 *d_in, in
         p.gain_f = h->d_gain_f;
         p.gain_d = h->d_gain_d;
         p.out_stride = stride;
+        p.out2 = h->d_out2;
+        p.out2_stride = 2LL * h->max_blocks;
+        p.n_main = h->n_sel;
         p.state_len = state_len;
         p.n_in = n_in;
         p.M = h->M;
@@ -607,7 +789,7 @@ sdrgpu_status sdrgpu::chan_enqueue(sdrgpu_channelizer *h, const float2 *d_in, in
         p.H = h->H;
         p.n_blocks = n_blocks;
         p.parity0 = h->parity0;
-        p.n_sel = h->n_sel;
+        p.n_sel = h->n_rows;
         p.layout = layout;
         p.gain_exact = h->gain_exact;
         p.identity = h->identity;
@@ -631,6 +813,12 @@ sdrgpu_status sdrgpu::chan_enqueue(sdrgpu_channelizer *h, const float2 *d_in, in
         else st = (h->T == 9) ? launch_pfb<8, 9>(h, p, grid) : launch_pfb<8, 0>(h, p, grid);
         h->timer.end(h->stream);
         SDRGPU_TRY(st);
+        if (layout == SDRGPU_LAYOUT_CHANNELS && h->n_post > 0) {
+            post_channel_kernel<<<h->n_post, 32, 0, h->stream>>>(d_out, stride, h->d_out2, 2LL * h->max_blocks, n_blocks, h->d_post,
+                                                                 h->d_post_state, h->synth);
+            count_launch();
+            SDRGPU_CUDA(cudaGetLastError());
+        }
     }
     // carry the history + leftover over to the next call
     const int consumed = n_blocks * h->half;
@@ -783,6 +971,9 @@ sdrgpu_status sdrgpu_chan_destroy(sdrgpu_channelizer *h)
     cudaFree(h->d_sel);
     cudaFree(h->d_gain_f);
     cudaFree(h->d_gain_d);
+    cudaFree(h->d_post);
+    cudaFree(h->d_post_state);
+    cudaFree(h->d_out2);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     if (h->copy_in) cudaStreamDestroy(h->copy_in);
     if (h->copy_out) cudaStreamDestroy(h->copy_out);
@@ -809,17 +1000,44 @@ sdrgpu_status sdrgpu_chan_sync(sdrgpu_channelizer *h)
     return SDRGPU_OK;
 }
 
+sdrgpu_status sdrgpu_chan_set_sample_rate(sdrgpu_channelizer *h, double sample_rate)
+{
+    if (!h) return fail(SDRGPU_ERR_INVALID_ARG, "NULL handle");
+    if (!(sample_rate > 0.0)) return fail(SDRGPU_ERR_INVALID_ARG, "sample rate must be positive");
+    h->sample_rate = sample_rate;
+    return SDRGPU_OK;
+}
+
 sdrgpu_status sdrgpu_chan_select(sdrgpu_channelizer *h, const sdrgpu_output_channel *channels, int n_channels,
                                  const float *synthesis_filter, int n_synthesis_taps)
 {
     if (!h || !channels || n_channels <= 0) return fail(SDRGPU_ERR_INVALID_ARG, "NULL / empty selection");
-    (void)synthesis_filter;
-    (void)n_synthesis_taps;
+    bool any_two = false, any_special = false;
     for (int i = 0; i < n_channels; i++) {
         if (channels[i].bin1 < 0 || channels[i].bin1 >= h->M)
             return fail(SDRGPU_ERR_INVALID_ARG, "Channel [%d] is not valid -- max channel is %d", channels[i].bin1, h->M);
-        if (channels[i].bin2 >= 0 || channels[i].frequency_offset_hz != 0)
-            return fail(SDRGPU_ERR_INVALID_ARG, "two-bin / frequency-corrected output channels are not built yet");
+        if (channels[i].bin2 >= h->M)
+            return fail(SDRGPU_ERR_INVALID_ARG, "Channel [%d] is not valid -- max channel is %d", channels[i].bin2, h->M);
+        any_two |= channels[i].bin2 >= 0;
+        any_special |= channels[i].bin2 >= 0 || channels[i].frequency_offset_hz != 0;
+    }
+    if (any_special && !(h->sample_rate > 0.0))
+        return fail(SDRGPU_ERR_BAD_STATE, "two-bin / frequency-corrected channels need sdrgpu_chan_set_sample_rate first");
+    if (any_two) {
+        if (!synthesis_filter || n_synthesis_taps < 2)
+            return fail(SDRGPU_ERR_INVALID_ARG, "two-bin channels need the synthesis filter (getSincM2Synthesizer)");
+        // TwoChannelSynthesizerM2.init (:74-88): tapsPerChannel = ceil(filter.length / 2) with integer division; the
+        // I/Q-duplicated filter has 2 * tapsPerChannel * 2 entries
+        const int entries = n_synthesis_taps / 2;
+        if (entries > kMaxSynthEntries)
+            return fail(SDRGPU_ERR_INVALID_ARG, "synthesis filter longer than %d taps", 2 * kMaxSynthEntries);
+        std::memset(&h->synth, 0, sizeof(h->synth));
+        h->synth.entries = entries;
+        int fp = 0;
+        for (int cp = 0; cp < n_synthesis_taps && fp + 1 < 4 * entries; cp++) {
+            h->synth.f[fp++] = synthesis_filter[cp];
+            h->synth.f[fp++] = synthesis_filter[cp];
+        }
     }
     SDRGPU_CUDA(cudaStreamSynchronize(h->stream));
     h->channels.assign(channels, channels + n_channels);

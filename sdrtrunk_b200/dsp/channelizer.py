@@ -115,6 +115,7 @@ class ComplexPolyphaseChannelizerM2:
         self._h = C.c_void_p()
         native.check(native.lib().sdrgpu_chan_create(C.byref(self._h), taps.ctypes.data_as(C.POINTER(C.c_float)),
                                                      taps.size, self.mChannelCount, self._max_input_floats))
+        native.check(native.lib().sdrgpu_chan_set_sample_rate(self._h, self.mSampleRate))
         self._n_selected = self.mChannelCount
 
     # ---- reference API
@@ -150,6 +151,34 @@ class ComplexPolyphaseChannelizerM2:
             arr[i] = native.OutputChannel(int(b), -1, 0, gain)
         native.check(native.lib().sdrgpu_chan_select(self._h, arr, len(bins), None, 0))
         self._n_selected = len(bins)
+
+    POLYPHASE_SYNTHESIZER_TAPS_PER_CHANNEL = 9   # PolyphaseChannelManager.java
+
+    def setOutputChannels(self, channels, synthesisFilter=None):
+        """General selection: `channels` is a list of (indexes, frequencyOffsetHz[, gain]) where indexes is the 1- or
+        2-element list ChannelCalculator.getChannelIndexes returns (PolyphaseChannelManager.getOutputProcessor,
+        :198-222: One/TwoChannelOutputProcessor, gain = channel count).  The two-channel synthesis filter defaults to
+        getSincM2Synthesizer(channelSampleRate, channelBandwidth, 2, 9) (getOutputProcessorFilter, :491-504)."""
+        arr = (native.OutputChannel * len(channels))()
+        any_two = False
+        for i, ch in enumerate(channels):
+            indexes, offset = ch[0], ch[1]
+            gain = float(ch[2]) if len(ch) > 2 else float(self.mChannelCount)
+            if len(indexes) not in (1, 2):
+                raise native.IllegalArgumentException(
+                    "Request to create an output processor for unexpected channel index size:%d" % len(indexes))
+            any_two |= len(indexes) == 2
+            arr[i] = native.OutputChannel(int(indexes[0]), int(indexes[1]) if len(indexes) == 2 else -1, int(offset), gain)
+        filt, n_filt = None, 0
+        if any_two:
+            if synthesisFilter is None:
+                synthesisFilter = FilterFactory.getSincM2Synthesizer(self.getChannelSampleRate(),
+                                                                     self.mSampleRate / self.mChannelCount, 2,
+                                                                     self.POLYPHASE_SYNTHESIZER_TAPS_PER_CHANNEL)
+            self._synth = native.f32(synthesisFilter)
+            filt, n_filt = self._synth.ctypes.data_as(C.POINTER(C.c_float)), self._synth.size
+        native.check(native.lib().sdrgpu_chan_select(self._h, arr, len(channels), filt, n_filt))
+        self._n_selected = len(channels)
 
     def receiveChannels(self, samples, samples_mem=native.HOST, out=None, out_mem=native.HOST, out_stride_floats=None):
         """Returns float32 [n_selected, 2*n_blocks]: each row one channel's interleaved I/Q stream."""

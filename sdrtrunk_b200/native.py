@@ -85,6 +85,7 @@ PROTOTYPES = {
     "sdrgpu_chan_destroy": (C.c_int, [_vp]),
     "sdrgpu_chan_set_stream": (C.c_int, [_vp, _vp]),
     "sdrgpu_chan_sync": (C.c_int, [_vp]),
+    "sdrgpu_chan_set_sample_rate": (C.c_int, [_vp, C.c_double]),
     "sdrgpu_chan_select": (C.c_int, [_vp, C.POINTER(OutputChannel), C.c_int, _f32p, C.c_int]),
     "sdrgpu_chan_process": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, C.c_longlong, C.c_int, C.c_int, _i32p]),
     "sdrgpu_chan_blocks_for": (C.c_int, [_vp, C.c_int]),

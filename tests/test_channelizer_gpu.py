@@ -169,3 +169,50 @@ def test_device_resident_io(gpu):
     assert np.array_equal(back, host)
     L.sdrgpu_device_free(d_in)
     L.sdrgpu_device_free(d_out)
+
+
+def test_frequency_offset_and_two_channel_output_processors(gpu):
+    """a6 / a7: OneChannelOutputProcessor with the frequency-correction Oscillator and TwoChannelOutputProcessor
+    (TwoChannelSynthesizerM2 + FS4DownConverter + Oscillator) against the oracle, fed the oracle's own float32
+    channelizer results re-created by the GPU channelizer (the rows differ only by the inverse DFT's rounding, so the
+    comparison is at the 1e-4 relative-RMS bar), across ragged calls (state carried: oscillator, serpentine, fs/4)."""
+    from sdrtrunk_b200.dsp import ComplexPolyphaseChannelizerM2
+    m, fs = 96, 2.4e6
+    rng = np.random.default_rng(21)
+    taps = oracle.sinc_m2_channelizer(25000.0, m, 9)
+    synth = oracle.sinc_m2_synthesizer(50000.0, 25000.0, 2, 9)
+    n = 48 * 700
+    z = sg.awgn(rng, n, 1e-3)
+    z = z + sg.tone(fs, 7 * 25000.0 + 900.0, n, 0.2) + sg.tone(fs, 20 * 25000.0 + 12500.0 - 2500.0, n, 0.3)
+    z = z + sg.tone(fs, -5 * 25000.0 - 12500.0 + 4000.0, n, 0.25)      # straddles bins 90 / 91
+    x = sg.interleave(z)
+    res = oracle.Channelizer(taps, m).receive(x, mode="f64")
+
+    ch = ComplexPolyphaseChannelizerM2(taps, int(fs), m)
+    ch.setOutputChannels([([7], 900), ([20, 21], -2500), ([3], 0), ([90, 91], 0), ([40], -1234, 2.5)], synth)
+    parts, pos = [], 0
+    for cut in (2 * 48 * 100, 2 * 48 * 33 + 10, 2 * 48 * 300, x.size):
+        cut = min(cut + pos, x.size)
+        parts.append(ch.receiveChannels(x[pos:cut]))
+        pos = cut
+    got = np.concatenate(parts, axis=1)
+    assert got.shape == (5, 2 * res.shape[0])
+
+    one = oracle.OneChannelOutputProcessor(50000.0, 7, float(m))
+    one.set_frequency_offset(900)
+    two = oracle.TwoChannelOutputProcessor(50000.0, 20, 21, synth, float(m))
+    two.set_frequency_offset(-2500)
+    plain = oracle.OneChannelOutputProcessor(50000.0, 3, float(m))
+    two0 = oracle.TwoChannelOutputProcessor(50000.0, 90, 91, synth, float(m))
+    one_g = oracle.OneChannelOutputProcessor(50000.0, 40, 2.5)
+    one_g.set_frequency_offset(-1234)
+    want = [one.process(res), two.process(res), plain.process(res), two0.process(res), one_g.process(res)]
+    for i in range(5):
+        assert sg.rel_rms(got[i], want[i]) < TOL, i
+    # the corrected one-bin channel: the 900 Hz residual is mixed to DC (Oscillator conjugate rotation at -900 Hz ...)
+    c = sg.deinterleave(want[0][200:])
+    assert abs(np.angle(np.mean(c[1:] * np.conj(c[:-1])))) < 2 * np.pi * 2000 / 50000.0
+    # errors as the Java: more than two indexes / synthesis filter missing
+    from sdrtrunk_b200 import native
+    with pytest.raises(native.IllegalArgumentException):
+        ch.setOutputChannels([([1, 2, 3], 0)])
