@@ -293,6 +293,24 @@ class _ComplexDecimationFilter(_LazyBank):
     decimate = decimateComplex
 
 
+class _RealDecimationFilter(_LazyBank):
+    """IRealDecimationFilter.decimateReal(float[]): the real stream rides the I rail of the complex cascade (the
+    half-band arithmetic is per rail, RealHalfBandDecimationFilter.java:61-111 == the complex one with Q absent)"""
+
+    def __init__(self, rate, sampleRate=50000.0):
+        self.rate = rate
+        super().__init__(sample_rate=sampleRate, decimation=rate)
+
+    def decimateReal(self, samples):
+        samples = native.f32(samples)
+        if self.rate and samples.size % self.rate != 0:
+            raise native.IllegalArgumentException(
+                "Sample buffer length [%d] must be an integer multiple of %d" % (samples.size, self.rate))
+        iq = np.zeros(2 * samples.size, np.float32)
+        iq[0::2] = samples
+        return self._get(samples.size).process(iq.reshape(1, -1))[0][0::2].copy()
+
+
 class DecimationFilterFactory:
     SUPPORTED_RATES = (0, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024)
 
@@ -302,6 +320,13 @@ class DecimationFilterFactory:
             raise native.IllegalArgumentException("Unsupported decimation rate: %d.  Supported decimation rates are:%s" %
                                                   (decimationRate, DecimationFilterFactory.SUPPORTED_RATES))
         return _ComplexDecimationFilter(decimationRate)
+
+    @staticmethod
+    def getRealDecimationFilter(decimationRate):
+        if decimationRate not in DecimationFilterFactory.SUPPORTED_RATES:
+            raise native.IllegalArgumentException("Unsupported decimation rate: %d.  Supported decimation rates are:%s" %
+                                                  (decimationRate, DecimationFilterFactory.SUPPORTED_RATES))
+        return _RealDecimationFilter(decimationRate)
 
 
 class FMDemodulator(_LazyBank):

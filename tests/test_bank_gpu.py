@@ -107,6 +107,10 @@ def test_single_channel_drop_in_classes(gpu):
     assert np.array_equal(ComplexFeedForwardGainControl(32).filter(x[:2048]), oracle.agc_block(x[:2048]))
     d = DecimationFilterFactory.getComplexDecimationFilter(4)
     assert np.array_equal(d.decimateComplex(x), oracle.Decimator(4).decimate_complex(x))
+    rd = DecimationFilterFactory.getRealDecimationFilter(8)
+    ref_rd = oracle.Decimator(8)
+    for _ in range(2):
+        assert np.array_equal(rd.decimateReal(r[:1600]), ref_rd.decimate_real(r[:1600]))
     with pytest.raises(native.IllegalArgumentException):
         DecimationFilterFactory.getComplexDecimationFilter(3)       # DecimationFilterFactory.java:62-64
     with pytest.raises(native.IllegalArgumentException):
@@ -305,3 +309,49 @@ def test_pipeline_channelizer_to_c4fm_bank(gpu):
         want_full = oracle.P25Chain(oracle.C4FM, 50000.0, fir).receive(y[: n_ch * 2])
         assert got[i].size == want_full.size
         assert np.array_equal(got[i][200:], want_full[200:]), k
+
+
+def test_config1_nbfm_chain(gpu):
+    """BASELINE configs[0] / SURVEY 8d config 1: 2.4 MS/s -> channelizer M = 96 -> bin 4 (50 kHz) -> ComplexDecimateX2
+    -> 25 kHz -> 45-tap low-pass -> squelching FM discriminator, fused on the device, against the oracle chain.
+    Tolerances (north_star): 25 kHz I/Q and demodulated floats 1e-4 relative RMS."""
+    from sdrtrunk_b200.dsp import Bank, ComplexPolyphaseChannelizerM2, Pipeline
+    m, fs = 96, 2.4e6
+    rng = np.random.default_rng(1)
+    n = 48 * 1024 * 6                                  # 6 assembler buffers of channel samples
+    t = np.arange(n) / fs
+    carrier = 0.5 * np.exp(1j * (2.5 * np.sin(2 * np.pi * 1000.0 * t) + 2 * np.pi * 100000.0 * t))   # +/-2.5 kHz dev.
+    x = sg.interleave(carrier + sg.awgn(rng, n, 1e-3))
+    taps = oracle.sinc_m2_channelizer(25000.0, m, 9)
+    fir = ss.remez(45, [0, 5000, 6250, 12500], [1, 0], fs=25000).astype(np.float32)
+
+    def gpu_chain(demod):
+        chan = ComplexPolyphaseChannelizerM2(taps, int(fs), m)
+        chan.setChannels([4])
+        if demod:
+            bank = Bank.preset(gpu.PRESET_NBFM, 1, 50000.0, fir, max_samples_per_call=8192)
+        else:
+            bank = Bank(1, 50000.0, fir_taps=fir, decimation=2, max_samples_per_call=8192)
+        assert bank.decimation == 2
+        pipe = Pipeline(chan, bank)
+        cut = x.size // 3 // 2 * 2
+        return np.concatenate([pipe.process(x[:cut]), pipe.process(x[cut:])], axis=1)[0]
+
+    res = oracle.Channelizer(taps, m).receive(x, mode="f64")
+    y = oracle.OneChannelOutputProcessor(50000.0, 4, float(m)).process(res)
+    dec, f, fm = oracle.Decimator(2), oracle.ComplexFIR(fir), oracle.SquelchingFMDemodulator(0.0004, -78.0, 4)
+    iq25, audio = [], []
+    for b in range(y.size // 2048):
+        d = f.filter(dec.decimate_complex(y[2048 * b:2048 * (b + 1)]))
+        iq25.append(d)
+        audio.append(fm.demodulate(d))
+    iq25, audio = np.concatenate(iq25), np.concatenate(audio)
+
+    got_iq = gpu_chain(False)
+    assert got_iq.shape == iq25.shape and sg.rel_rms(got_iq, iq25) < TOL
+    got = gpu_chain(True)
+    assert got.shape == audio.shape
+    assert sg.rel_rms(got, audio) < TOL
+    assert np.max(np.abs(got - audio)) < 1e-5
+    # it is the 1 kHz tone at +/-2.5 kHz deviation: peak angle per 25 kHz sample = 2 pi 2500 / 25000
+    assert abs(np.max(got[1000:]) - 2 * np.pi * 2500 / 25000) < 2e-2
