@@ -15,7 +15,7 @@ cat $out/${tag}_bench.json
 python bench.py --impl reference --steps 3 --warmup 1 > $out/${tag}_bench_reference.json 2> $out/${tag}_bench_reference.err
 cat $out/${tag}_bench_reference.json
 if [ "$2" != "noncu" ]; then
-CMD="python bench.py --workload c4fm --steps 1 --warmup 3 --no-cpu-baseline"
+CMD="python bench.py --workload c4fm --steps 1 --warmup 3 --no-cpu-baseline --device-only"
 $CMD > $out/${tag}_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/${tag}_launches.csv $CMD > $out/${tag}_ncu1.log 2>&1
 $CMD > $out/${tag}_plain2.log 2>&1 &&
