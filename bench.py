@@ -367,13 +367,24 @@ class GpuWorkload:
     def step_host(self):
         n, L = self.native, self.L
         if self.pipeline is None:
-            n.check(L.sdrgpu_chan_process(self.chan._h, C.c_void_p(self.x_host.data_ptr()), self.n_floats, n.HOST,
+            n.check(L.sdrgpu_chan_process(self.chan._h, C.c_void_p(getattr(self, '_host_in', self.x_host).data_ptr()), self.n_floats, n.HOST,
                                           C.c_void_p(self.out_host.data_ptr()), 2 * self.n_blocks, n.HOST,
                                           n.LAYOUT_CHANNELS, None))
         else:
-            n.check(L.sdrgpu_pipeline_process(self.pipeline._h, C.c_void_p(self.x_host.data_ptr()), self.n_floats,
-                                              n.HOST, C.c_void_p(self.sym_host.data_ptr()), self.sym_stride, None, 0,
+            n.check(L.sdrgpu_pipeline_process(self.pipeline._h, C.c_void_p(getattr(self, '_host_in', self.x_host).data_ptr()),
+                                              self.n_floats, n.HOST, C.c_void_p(self.sym_host.data_ptr()), self.sym_stride, None, 0,
                                               C.c_void_p(self.cnt_host.data_ptr()), n.HOST))
+
+    def enable_u8_input(self, on):
+        """section 8f #1: the tuner's native unsigned 8-bit samples, converted on the device (4x less H2D)"""
+        torch = self.torch
+        if on and not hasattr(self, "x_host_u8"):
+            q = torch.clamp(torch.round(self.x_dev * 128.0 + 127.0), 0, 255).to(torch.uint8)
+            self.x_host_u8 = torch.empty(self.n_floats, dtype=torch.uint8, pin_memory=True)
+            self.x_host_u8.copy_(q)
+            del q
+        self.chan.setSampleFormat("u8" if on else "f32")
+        self._host_in = self.x_host_u8 if on else self.x_host
 
     def sanity(self):
         """decoded-vs-transmitted dibits of a few channels (first pass from reset state would be needed for an exact
@@ -440,13 +451,22 @@ def measure(w, args, world, dist, barrier):
         ms_e2e_dev, wall_e2e = ms_dev, ms_dev
     else:
         ms_e2e_dev, wall_e2e = timed(w.step_host, args.steps, max(3, args.warmup))
+    e2e_u8 = None
+    if not args.device_only:
+        w.enable_u8_input(True)
+        ms_u8_dev, wall_u8 = timed(w.step_host, args.steps, 3)
+        w.enable_u8_input(False)
+        u8_ms = max(ms_u8_dev, wall_u8) / args.steps
+        e2e_u8 = {"value": w.n_complex * world / (u8_ms * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": w.n_floats,
+                  "d2h_bytes_per_step": w.d2h, "ms_per_step": u8_ms,
+                  "input": "unsigned 8-bit tuner samples (ByteSampleConverter format), converted on the device"}
     kernels = w.kernel_times(min(args.steps, 10))
     ms_per_step = ms_dev / args.steps
     total = w.n_complex * world
     e2e_ms = max(ms_e2e_dev, wall_e2e) / args.steps
     return {"ms_per_step": ms_per_step, "value": total / (ms_per_step * 1e-3) / 1e6,
             "e2e_ms": e2e_ms, "e2e_value": total / (e2e_ms * 1e-3) / 1e6, "launches": launches, "kernels": kernels,
-            "sanity": sanity}
+            "sanity": sanity, "e2e_u8": e2e_u8}
 
 
 def run_gpu(args, rank, world, local_rank):
@@ -510,6 +530,7 @@ def run_gpu(args, rank, world, local_rank):
                  "realtime_channels": m * world * (r2["value"] / world) / (fs / 1e6),
                  "e2e": {"value": r2["e2e_value"], "unit": UNIT, "h2d_bytes_per_step": w2.h2d,
                          "d2h_bytes_per_step": w2.d2h, "ms_per_step": r2["e2e_ms"]},
+                 "e2e_u8_input": r2["e2e_u8"],
                  "gpu_launches": r2["launches"], "kernels_ms": r2["kernels"], "roofline": roofline_of(w2, r2),
                  "decode_sanity": r2["sanity"]}
         del w2
@@ -536,6 +557,7 @@ def run_gpu(args, rank, world, local_rank):
         "realtime_channels": m * world * (r["value"] / world) / (fs / 1e6),
         "e2e": {"value": r["e2e_value"], "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": r["e2e_ms"]},
+        "e2e_u8_input": r["e2e_u8"],
         "gpu_launches": r["launches"],
         "roofline": main_roofline,
         "cpu_baseline": base,

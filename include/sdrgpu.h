@@ -76,6 +76,16 @@ sdrgpu_status sdrgpu_channel_indexes(double sample_rate, int channel_count, doub
 sdrgpu_status sdrgpu_center_frequency_for_indexes(double sample_rate, int channel_count, double center_frequency,
                                                   const int *indexes, int n_indexes, long long *frequency);
 
+/* ------------------------------------------------------------------ tuner sample formats
+ * The native formats the tuner converters turn into float I/Q before the channelizer: unsigned 8-bit
+ * (J/source/tuner/usb/converter/ByteSampleConverter.java:21-35: (x - 127) / 128.0f), signed 8-bit
+ * (SignedByteSampleConverter.java:21-35: x / 128.0f), little-endian signed 16-bit
+ * (J/sample/ConversionUtils.java:22-34: x / 32767.0f).  Converting on the device cuts the host-to-device copy to
+ * 1-2 bytes per value instead of 4. */
+enum { SDRGPU_FORMAT_F32 = 0, SDRGPU_FORMAT_U8 = 1, SDRGPU_FORMAT_S8 = 2, SDRGPU_FORMAT_S16LE = 3 };
+/* n_values sample values (I and Q count separately) from src (format) to float dst */
+sdrgpu_status sdrgpu_convert_samples(int format, const void *src, int src_mem, int n_values, float *dst, int dst_mem);
+
 /* ------------------------------------------------------------------ polyphase channelizer
  * Replaces ComplexPolyphaseChannelizerM2.receive + process + IFFTProcessor
  * (J/dsp/filter/channelizer/ComplexPolyphaseChannelizerM2.java:190-235,337-383,407-428) and, in channel
@@ -98,6 +108,10 @@ sdrgpu_status sdrgpu_chan_sync(sdrgpu_channelizer *h);
 /* tuner sample rate in Hz (the sampleRate argument of the ComplexPolyphaseChannelizerM2 constructors / setRates,
  * :93,114,169): needed before two-bin or frequency-corrected channels are selected (channel rate = 2 * rate / M) */
 sdrgpu_status sdrgpu_chan_set_sample_rate(sdrgpu_channelizer *h, double sample_rate);
+
+/* format of the `iq` buffers of sdrgpu_chan_process / sdrgpu_pipeline_process (default SDRGPU_FORMAT_F32): with a
+ * native format `iq` points at the raw bytes and n_floats still counts sample values */
+sdrgpu_status sdrgpu_chan_set_input_format(sdrgpu_channelizer *h, int format);
 
 /* One output channel of the channel layout: one polyphase bin (bin2 < 0; OneChannelOutputProcessor) or two
  * adjacent bins recombined (TwoChannelOutputProcessor); frequency_offset_hz drives the frequency-correction
@@ -126,7 +140,7 @@ enum {
  * calls like mSampleBufferPointer, :202-227).  *n_blocks receives the number of output blocks
  * (= complex samples per output channel) produced by this call.  out_stride_floats is only used by the
  * channel layout (row pitch in floats, >= 2 * blocks). */
-sdrgpu_status sdrgpu_chan_process(sdrgpu_channelizer *h, const float *iq, int n_floats, int in_mem, float *out,
+sdrgpu_status sdrgpu_chan_process(sdrgpu_channelizer *h, const void *iq, int n_floats, int in_mem, float *out,
                                   long long out_stride_floats, int out_mem, int layout, int *n_blocks);
 /* how many blocks a call with n_floats would produce now */
 int sdrgpu_chan_blocks_for(const sdrgpu_channelizer *h, int n_floats);
@@ -218,7 +232,7 @@ sdrgpu_status sdrgpu_bank_last_kernel_ms(sdrgpu_bank *b, float *ms2);
 typedef struct sdrgpu_pipeline sdrgpu_pipeline;
 sdrgpu_status sdrgpu_pipeline_create(sdrgpu_pipeline **p, sdrgpu_channelizer *chan, sdrgpu_bank *bank);
 sdrgpu_status sdrgpu_pipeline_destroy(sdrgpu_pipeline *p); /* does not destroy chan / bank */
-sdrgpu_status sdrgpu_pipeline_process(sdrgpu_pipeline *p, const float *iq, int n_floats, int in_mem,
+sdrgpu_status sdrgpu_pipeline_process(sdrgpu_pipeline *p, const void *iq, int n_floats, int in_mem,
                                       uint8_t *symbols, int symbol_stride, float *demod,
                                       long long demod_stride_floats, int *counts, int out_mem);
 

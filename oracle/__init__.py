@@ -62,6 +62,9 @@ def lib():
         "orc_chan_receive_raw": (C.c_int, [vp, _f32p, C.c_int, _f32p]),
         "orc_calc_channel_indexes": (C.c_int, [C.POINTER(_Calc), C.c_longlong, C.c_int, _i32p, C.c_int]),
         "orc_calc_center_frequency_for_indexes": (C.c_longlong, [C.POINTER(_Calc), _i32p, C.c_int]),
+        "orc_convert_u8": (None, [C.c_void_p, C.c_int, _f32p]),
+        "orc_convert_s8": (None, [C.c_void_p, C.c_int, _f32p]),
+        "orc_convert_s16le": (None, [C.c_void_p, C.c_int, _f32p]),
         "orc_get_channel": (None, [_f32p, C.c_int, C.c_int, C.c_int, _f32p]),
         "orc_apply_gain": (None, [_f32p, C.c_int, C.c_double]),
         "orc_one_channel_create": (vp, [C.c_double, C.c_int, C.c_double]),
@@ -153,6 +156,17 @@ def kaiser(length, attenuation):
 def evaluate(taps, frequency):
     a, p = _f32(taps)
     return lib().orc_evaluate(p, a.size, frequency)
+
+
+# ---------------------------------------------------------------- tuner sample converters
+def convert_samples(raw, fmt):
+    """fmt: 'u8' (ByteSampleConverter), 's8' (SignedByteSampleConverter), 's16le' (ConversionUtils); raw: bytes-like"""
+    a = np.ascontiguousarray(np.frombuffer(bytes(raw), dtype=np.uint8))
+    n = a.size // (2 if fmt == "s16le" else 1)
+    out = np.zeros(n, np.float32)
+    fn = {"u8": lib().orc_convert_u8, "s8": lib().orc_convert_s8, "s16le": lib().orc_convert_s16le}[fmt]
+    fn(a.ctypes.data_as(C.c_void_p), n, out.ctypes.data_as(_f32p))
+    return out
 
 
 # ---------------------------------------------------------------- FFT

@@ -222,3 +222,25 @@ void orc_two_channel_process(orc_two_channel *p, const float *results, int n_blo
     orc_osc_mix(&p->osc, out, 2 * n_blocks);
     orc_apply_gain(out, 2 * n_blocks, p->gain);
 }
+
+/* ---------------------------------------------------------------- tuner sample converters
+ * ByteSampleConverter.java:21-35 (LOOKUP_VALUES[x] = (float)(x - 127) / 128.0f),
+ * SignedByteSampleConverter.java:21-35 ((float)((byte)x) / 128.0f),
+ * ConversionUtils.java:22-34 (little-endian short / (float)Short.MAX_VALUE) */
+void orc_convert_u8(const uint8_t *in, int n, float *out)
+{
+    for (int x = 0; x < n; x++) out[x] = (float)((int)in[x] - 127) / 128.0f;
+}
+
+void orc_convert_s8(const int8_t *in, int n, float *out)
+{
+    for (int x = 0; x < n; x++) out[x] = (float)in[x] / 128.0f;
+}
+
+void orc_convert_s16le(const uint8_t *in, int n, float *out)
+{
+    for (int x = 0; x < n; x++) {
+        short v = (short)((unsigned)in[2 * x] | ((unsigned)in[2 * x + 1] << 8));
+        out[x] = (float)v / (float)32767;
+    }
+}

@@ -97,6 +97,11 @@ void orc_two_channel_destroy(orc_two_channel *p);
 void orc_two_channel_set_frequency_offset(orc_two_channel *p, long long offset);
 void orc_two_channel_process(orc_two_channel *p, const float *results, int n_blocks, int m, float *out);
 
+/* ---------------------------------------------------------------- tuner sample converters (section 8f #1) */
+void orc_convert_u8(const uint8_t *in, int n, float *out);
+void orc_convert_s8(const int8_t *in, int n, float *out);
+void orc_convert_s16le(const uint8_t *in, int n, float *out);
+
 /* ---------------------------------------------------------------- decimation (a9, a10) */
 typedef struct orc_halfband orc_halfband;
 orc_halfband *orc_halfband_create(const float *coefficients, int length);

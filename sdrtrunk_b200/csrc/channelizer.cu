@@ -583,6 +583,24 @@ __global__ void __launch_bounds__(32) post_channel_kernel(float *out, long long 
         for (int i = lane; i < H; i += 32) st->hist[i] = ent[i];
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// tuner sample converters (ByteSampleConverter / SignedByteSampleConverter lookup tables, ConversionUtils 16-bit)
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float convert_value(int format, const void *src, size_t i)
+{
+    if (format == SDRGPU_FORMAT_U8) return __fdiv_rn((float)((int)reinterpret_cast<const uint8_t *>(src)[i] - 127), 128.0f);
+    if (format == SDRGPU_FORMAT_S8) return __fdiv_rn((float)reinterpret_cast<const int8_t *>(src)[i], 128.0f);
+    const uint8_t *b = reinterpret_cast<const uint8_t *>(src) + 2 * i;   // little endian, any alignment
+    const short v = (short)((unsigned)b[0] | ((unsigned)b[1] << 8));
+    return __fdiv_rn((float)v, 32767.0f);
+}
+
+__global__ void convert_kernel(int format, const void *__restrict__ src, float *__restrict__ dst, size_t n)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        dst[i] = convert_value(format, src, i);
+}
+
 // new_state[i] = S[consumed + i], S = [state | in]
 __global__ void save_state_kernel(const float2 *state, int state_len, const float2 *in, int n_in, int consumed,
                                   float2 *new_state, int new_len)
@@ -621,7 +639,9 @@ struct sdrgpu_channelizer {
     int fast_r1 = 0, fast_r2 = 0;  // factors of the pfb2 fast path (0 = generic kernel)
     float2 *d_state[2] = {nullptr, nullptr};
     int cur_state = 0;
-    float2 *d_in = nullptr;    // staging for host input
+    float2 *d_in = nullptr;    // staging for host input (float I/Q)
+    uint8_t *d_raw = nullptr;  // staging for host input in a native tuner format
+    int in_format = SDRGPU_FORMAT_F32;
     float *d_out = nullptr;    // staging for host output
     size_t d_out_bytes = 0;
     int n_sel = 0;
@@ -839,10 +859,42 @@ sdrgpu_status sdrgpu::chan_enqueue(sdrgpu_channelizer *h, const float2 *d_in, in
 }
 
 cudaStream_t sdrgpu::chan_stream(const sdrgpu_channelizer *h) { return h->stream; }
-float2 *sdrgpu::chan_staging_in(sdrgpu_channelizer *h)
+
+size_t sdrgpu::chan_value_bytes(const sdrgpu_channelizer *h)
 {
+    return h->in_format == SDRGPU_FORMAT_F32 ? 4 : (h->in_format == SDRGPU_FORMAT_S16LE ? 2 : 1);
+}
+
+sdrgpu_status sdrgpu::chan_upload(sdrgpu_channelizer *h, const void *iq, size_t first, int n, cudaStream_t copy_stream)
+{
+    const size_t vb = chan_value_bytes(h);
+    if (!h->d_in) SDRGPU_CUDA(cudaMalloc(&h->d_in, sizeof(float2) * (size_t)h->max_in_complex));
+    void *dst = h->d_in + first;
+    if (h->in_format != SDRGPU_FORMAT_F32) {
+        if (!h->d_raw) SDRGPU_CUDA(cudaMalloc(&h->d_raw, 2 * vb * (size_t)h->max_in_complex));
+        dst = h->d_raw + 2 * vb * first;
+    }
+    SDRGPU_CUDA(cudaMemcpyAsync(dst, reinterpret_cast<const uint8_t *>(iq) + 2 * vb * first, 2 * vb * (size_t)n,
+                                cudaMemcpyHostToDevice, copy_stream));
+    return SDRGPU_OK;
+}
+
+const float2 *sdrgpu::chan_convert(sdrgpu_channelizer *h, const void *iq_device, size_t first, int n)
+{
+    const size_t vb = chan_value_bytes(h);
+    if (h->in_format == SDRGPU_FORMAT_F32)
+        return iq_device ? reinterpret_cast<const float2 *>(iq_device) + first : h->d_in + first;
     if (!h->d_in && cudaMalloc(&h->d_in, sizeof(float2) * (size_t)h->max_in_complex) != cudaSuccess) return nullptr;
-    return h->d_in;
+    const uint8_t *src = iq_device ? reinterpret_cast<const uint8_t *>(iq_device) : h->d_raw;
+    if (n > 0) {
+        const size_t values = 2 * (size_t)n;
+        int grid = (int)((values + 255) / 256);
+        if (grid > 148 * 16) grid = 148 * 16;
+        convert_kernel<<<grid, 256, 0, h->stream>>>(h->in_format, src + 2 * vb * first, reinterpret_cast<float *>(h->d_in + first),
+                                                    values);
+        count_launch();
+    }
+    return h->d_in + first;
 }
 int sdrgpu::chan_half(const sdrgpu_channelizer *h) { return h->half; }
 
@@ -967,6 +1019,7 @@ sdrgpu_status sdrgpu_chan_destroy(sdrgpu_channelizer *h)
     cudaFree(h->d_state[0]);
     cudaFree(h->d_state[1]);
     cudaFree(h->d_in);
+    cudaFree(h->d_raw);
     cudaFree(h->d_out);
     cudaFree(h->d_sel);
     cudaFree(h->d_gain_f);
@@ -997,6 +1050,41 @@ sdrgpu_status sdrgpu_chan_sync(sdrgpu_channelizer *h)
 {
     if (!h) return fail(SDRGPU_ERR_INVALID_ARG, "NULL handle");
     SDRGPU_CUDA(cudaStreamSynchronize(h->stream));
+    return SDRGPU_OK;
+}
+
+sdrgpu_status sdrgpu_chan_set_input_format(sdrgpu_channelizer *h, int format)
+{
+    if (!h) return fail(SDRGPU_ERR_INVALID_ARG, "NULL handle");
+    if (format < SDRGPU_FORMAT_F32 || format > SDRGPU_FORMAT_S16LE) return fail(SDRGPU_ERR_INVALID_ARG, "unknown sample format %d", format);
+    SDRGPU_CUDA(cudaStreamSynchronize(h->stream));
+    h->in_format = format;
+    return SDRGPU_OK;
+}
+
+sdrgpu_status sdrgpu_convert_samples(int format, const void *src, int src_mem, int n_values, float *dst, int dst_mem)
+{
+    if (format < SDRGPU_FORMAT_U8 || format > SDRGPU_FORMAT_S16LE) return fail(SDRGPU_ERR_INVALID_ARG, "unknown native sample format %d", format);
+    if (n_values < 0 || (n_values > 0 && (!src || !dst))) return fail(SDRGPU_ERR_INVALID_ARG, "NULL / negative argument");
+    if (n_values == 0) return SDRGPU_OK;
+    const size_t vb = format == SDRGPU_FORMAT_S16LE ? 2 : 1;
+    void *d_src = const_cast<void *>(src);
+    float *d_dst = dst;
+    if (src_mem == SDRGPU_HOST) {
+        SDRGPU_CUDA(cudaMalloc(&d_src, vb * (size_t)n_values));
+        SDRGPU_CUDA(cudaMemcpy(d_src, src, vb * (size_t)n_values, cudaMemcpyHostToDevice));
+    }
+    if (dst_mem == SDRGPU_HOST) SDRGPU_CUDA(cudaMalloc(&d_dst, sizeof(float) * (size_t)n_values));
+    int grid = (n_values + 255) / 256;
+    if (grid > 148 * 16) grid = 148 * 16;
+    convert_kernel<<<grid, 256>>>(format, d_src, d_dst, (size_t)n_values);
+    count_launch();
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && dst_mem == SDRGPU_HOST) e = cudaMemcpy(dst, d_dst, sizeof(float) * (size_t)n_values, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (src_mem == SDRGPU_HOST) cudaFree(d_src);
+    if (dst_mem == SDRGPU_HOST) cudaFree(d_dst);
+    if (e != cudaSuccess) return fail(SDRGPU_ERR_CUDA, "sample conversion failed: %s", cudaGetErrorString(e));
     return SDRGPU_OK;
 }
 
@@ -1062,7 +1150,7 @@ sdrgpu_status sdrgpu_chan_last_kernel_ms(sdrgpu_channelizer *h, float *ms)
     return h->timer.read(ms);
 }
 
-sdrgpu_status sdrgpu_chan_process(sdrgpu_channelizer *h, const float *iq, int n_floats, int in_mem, float *out,
+sdrgpu_status sdrgpu_chan_process(sdrgpu_channelizer *h, const void *iq, int n_floats, int in_mem, float *out,
                                   long long out_stride_floats, int out_mem, int layout, int *n_blocks_out)
 {
     if (!h) return fail(SDRGPU_ERR_INVALID_ARG, "NULL handle");
@@ -1074,7 +1162,7 @@ sdrgpu_status sdrgpu_chan_process(sdrgpu_channelizer *h, const float *iq, int n_
     if (n_in > h->max_in_complex)
         return fail(SDRGPU_ERR_OVERFLOW, "input of %d floats exceeds the handle's max_input_floats %d", n_floats,
                     2 * h->max_in_complex);
-    if (((uintptr_t)iq & 7) != 0 && in_mem == SDRGPU_DEVICE)
+    if (((uintptr_t)iq & 7) != 0 && in_mem == SDRGPU_DEVICE && h->in_format == SDRGPU_FORMAT_F32)
         return fail(SDRGPU_ERR_INVALID_ARG, "device input must be 8-byte aligned");
     SDRGPU_CUDA(cudaSetDevice(h->device));
 
@@ -1110,12 +1198,11 @@ sdrgpu_status sdrgpu_chan_process(sdrgpu_channelizer *h, const float *iq, int n_
         d_out = h->d_out;
         stride = 2LL * n_blocks;
     }
-    if (in_mem == SDRGPU_HOST && n_in > 0 && !h->d_in)
-        SDRGPU_CUDA(cudaMalloc(&h->d_in, sizeof(float2) * (size_t)h->max_in_complex));
-
     if (in_mem == SDRGPU_DEVICE && out_mem == SDRGPU_DEVICE) {
         int got = 0;
-        return sdrgpu::chan_enqueue(h, reinterpret_cast<const float2 *>(iq), n_in, out, out_stride_floats, layout, &got);
+        const float2 *src = sdrgpu::chan_convert(h, iq, 0, n_in);
+        if (!src && n_in > 0) return fail(SDRGPU_ERR_NOMEM, "cannot allocate the input staging buffer");
+        return sdrgpu::chan_enqueue(h, src, n_in, out, out_stride_floats, layout, &got);
     }
 
     // Host buffers: the call is cut into chunks so that the H2D copy of chunk i+1, the kernels of chunk i and the D2H
@@ -1129,15 +1216,17 @@ sdrgpu_status sdrgpu_chan_process(sdrgpu_channelizer *h, const float *iq, int n_
     int done_in = 0, done_blocks = 0, ci = 0;
     while (done_in < n_in || (n_in == 0 && ci == 0)) {
         const int n = (n_in - done_in < chunk) ? n_in - done_in : chunk;
-        const float2 *src_dev = reinterpret_cast<const float2 *>(iq) + done_in;
+        const float2 *src_dev = nullptr;
         cudaEvent_t ev_in = h->events[(2 * ci) % kMaxEvents], ev_k = h->events[(2 * ci + 1) % kMaxEvents];
         if (in_mem == SDRGPU_HOST && n > 0) {
-            SDRGPU_CUDA(cudaMemcpyAsync(h->d_in + done_in, iq + 2 * (size_t)done_in, sizeof(float2) * (size_t)n,
-                                        cudaMemcpyHostToDevice, h->copy_in));
+            SDRGPU_TRY(sdrgpu::chan_upload(h, iq, (size_t)done_in, n, h->copy_in));
             SDRGPU_CUDA(cudaEventRecord(ev_in, h->copy_in));
             SDRGPU_CUDA(cudaStreamWaitEvent(h->stream, ev_in, 0));
-            src_dev = h->d_in + done_in;
+            src_dev = sdrgpu::chan_convert(h, nullptr, (size_t)done_in, n);
+        } else {
+            src_dev = sdrgpu::chan_convert(h, iq, (size_t)done_in, n);
         }
+        if (!src_dev && n > 0) return fail(SDRGPU_ERR_NOMEM, "cannot allocate the input staging buffer");
         float *dst = nullptr;
         if (n_blocks > 0)
             dst = (layout == SDRGPU_LAYOUT_CHANNELS) ? d_out + 2 * (size_t)done_blocks : d_out + 2 * (size_t)done_blocks * h->M;

@@ -45,7 +45,12 @@ int chan_selected_count(const sdrgpu_channelizer *h);
 sdrgpu_status chan_enqueue(sdrgpu_channelizer *h, const float2 *d_in, int n_in, float *d_out, long long stride, int layout,
                            int *n_blocks_out);
 cudaStream_t chan_stream(const sdrgpu_channelizer *h);
-float2 *chan_staging_in(sdrgpu_channelizer *h);
+// host-buffer staging of the chunked paths: enqueue the H2D copy of complex samples [first, first + n) of the caller's
+// buffer (in the handle's input format) on copy_stream; then, on the handle's stream, convert them to float I/Q if the
+// format is a native one.  chan_convert returns the device float2 pointer of the chunk.
+sdrgpu_status chan_upload(sdrgpu_channelizer *h, const void *iq, size_t first, int n, cudaStream_t copy_stream);
+const float2 *chan_convert(sdrgpu_channelizer *h, const void *iq_device_or_null, size_t first, int n);
+size_t chan_value_bytes(const sdrgpu_channelizer *h);
 int chan_half(const sdrgpu_channelizer *h);
 
 inline void count_launch(int n = 1) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }

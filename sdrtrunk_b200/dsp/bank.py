@@ -186,7 +186,7 @@ class Pipeline:
         L = native.lib()
         bank = self.bank
         if samples_mem == native.HOST:
-            samples = native.f32(samples)
+            samples = np.ascontiguousarray(samples, dtype=getattr(self.channelizer, "_dtype", np.float32))
             n_floats = samples.size
             in_ptr = native.ptr(samples)
         else:

@@ -184,6 +184,15 @@ class ComplexPolyphaseChannelizerM2:
         """Returns float32 [n_selected, 2*n_blocks]: each row one channel's interleaved I/Q stream."""
         return self._process(samples, samples_mem, out, out_mem, native.LAYOUT_CHANNELS, out_stride_floats)
 
+    _FORMATS = {"f32": (native.FORMAT_F32, np.float32), "u8": (native.FORMAT_U8, np.uint8),
+                "s8": (native.FORMAT_S8, np.int8), "s16le": (native.FORMAT_S16LE, np.dtype("<i2"))}
+
+    def setSampleFormat(self, fmt):
+        """Native tuner sample format of the buffers given to receive / receiveChannels: 'f32' (default), 'u8'
+        (ByteSampleConverter), 's8' (SignedByteSampleConverter), 's16le' (ConversionUtils); converted on the device."""
+        code, self._dtype = self._FORMATS[fmt]
+        native.check(native.lib().sdrgpu_chan_set_input_format(self._h, code))
+
     def setStream(self, cuda_stream):
         native.check(native.lib().sdrgpu_chan_set_stream(self._h, C.c_void_p(int(cuda_stream) if cuda_stream else 0)))
 
@@ -204,7 +213,7 @@ class ComplexPolyphaseChannelizerM2:
     def _process(self, samples, samples_mem, out, out_mem, layout, out_stride_floats=None):
         L = native.lib()
         if samples_mem == native.HOST:
-            samples = native.f32(samples)
+            samples = np.ascontiguousarray(samples, dtype=getattr(self, "_dtype", np.float32))
             n_floats = samples.size
             in_ptr = native.ptr(samples)
         else:
@@ -236,3 +245,32 @@ class ComplexPolyphaseChannelizerM2:
             self.dispose()
         except Exception:
             pass
+
+
+class _SampleConverter:
+    """NativeBufferConverter.convertSamples(ByteBuffer, length) -> float[]: converts on the device"""
+    FORMAT, DTYPE = None, None
+
+    def convertSamples(self, nativeBuffer, length=None):
+        raw = np.ascontiguousarray(np.frombuffer(bytes(nativeBuffer), dtype=self.DTYPE))
+        n = raw.size if length is None else min(raw.size, int(length) // raw.itemsize)
+        out = np.empty(n, np.float32)
+        native.init(0)
+        native.check(native.lib().sdrgpu_convert_samples(self.FORMAT, native.ptr(raw), native.HOST, n, native.ptr(out),
+                                                         native.HOST))
+        return out
+
+
+class ByteSampleConverter(_SampleConverter):
+    """J/source/tuner/usb/converter/ByteSampleConverter.java"""
+    FORMAT, DTYPE = native.FORMAT_U8, np.uint8
+
+
+class SignedByteSampleConverter(_SampleConverter):
+    """J/source/tuner/usb/converter/SignedByteSampleConverter.java"""
+    FORMAT, DTYPE = native.FORMAT_S8, np.int8
+
+
+class Signed16BitSampleConverter(_SampleConverter):
+    """J/sample/ConversionUtils.java:22-34 convertFromSigned16BitSamples"""
+    FORMAT, DTYPE = native.FORMAT_S16LE, np.dtype("<i2")

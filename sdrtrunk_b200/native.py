@@ -15,6 +15,7 @@ HOST, DEVICE = 0, 1
 LAYOUT_RESULTS, LAYOUT_CHANNELS = 0, 1
 WINDOW_HAMMING, WINDOW_BLACKMAN = 0, 1
 DEMOD_NONE, DEMOD_FM, DEMOD_FM_SQUELCH, DEMOD_DQPSK_DECISION, DEMOD_DQPSK_GARDNER = 0, 1, 2, 3, 4
+FORMAT_F32, FORMAT_U8, FORMAT_S8, FORMAT_S16LE = 0, 1, 2, 3
 PRESET_P25_C4FM, PRESET_P25_LSM, PRESET_P25_HDQPSK, PRESET_NBFM = 0, 1, 2, 3
 
 OK, ERR_INVALID_ARG, ERR_BAD_STATE, ERR_CUDA, ERR_OVERFLOW, ERR_DESIGN, ERR_NOMEM = range(7)
@@ -85,6 +86,8 @@ PROTOTYPES = {
     "sdrgpu_chan_destroy": (C.c_int, [_vp]),
     "sdrgpu_chan_set_stream": (C.c_int, [_vp, _vp]),
     "sdrgpu_chan_sync": (C.c_int, [_vp]),
+    "sdrgpu_convert_samples": (C.c_int, [C.c_int, _vp, C.c_int, C.c_int, _vp, C.c_int]),
+    "sdrgpu_chan_set_input_format": (C.c_int, [_vp, C.c_int]),
     "sdrgpu_chan_set_sample_rate": (C.c_int, [_vp, C.c_double]),
     "sdrgpu_chan_select": (C.c_int, [_vp, C.POINTER(OutputChannel), C.c_int, _f32p, C.c_int]),
     "sdrgpu_chan_process": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, C.c_longlong, C.c_int, C.c_int, _i32p]),

@@ -216,3 +216,35 @@ def test_frequency_offset_and_two_channel_output_processors(gpu):
     from sdrtrunk_b200 import native
     with pytest.raises(native.IllegalArgumentException):
         ch.setOutputChannels([([1, 2, 3], 0)])
+
+
+@pytest.mark.parametrize("fmt", ["u8", "s8", "s16le"])
+def test_native_tuner_sample_formats(gpu, fmt):
+    """section 8f #1: ByteSampleConverter / SignedByteSampleConverter / 16-bit conversion on the device, standalone
+    (bit-exact: integer / power of two, or one correctly rounded division) and fused in front of the channelizer."""
+    from sdrtrunk_b200.dsp import (ByteSampleConverter, ComplexPolyphaseChannelizerM2, Signed16BitSampleConverter,
+                                   SignedByteSampleConverter)
+    rng = np.random.default_rng(31)
+    m = 96
+    n = 48 * 300
+    if fmt == "u8":
+        raw = rng.integers(0, 256, 2 * n, dtype=np.uint8)
+        conv = ByteSampleConverter()
+    elif fmt == "s8":
+        raw = rng.integers(-128, 128, 2 * n, dtype=np.int8)
+        conv = SignedByteSampleConverter()
+    else:
+        raw = rng.integers(-32768, 32768, 2 * n).astype("<i2")
+        conv = Signed16BitSampleConverter()
+    want_f = oracle.convert_samples(raw.tobytes(), fmt)
+    assert np.array_equal(conv.convertSamples(raw.tobytes()), want_f)
+    edge = {"u8": np.array([0, 127, 128, 255], np.uint8), "s8": np.array([-128, -1, 0, 127], np.int8),
+            "s16le": np.array([-32768, -1, 0, 32767], "<i2")}[fmt]
+    assert np.array_equal(conv.convertSamples(edge.tobytes()), oracle.convert_samples(edge.tobytes(), fmt))
+    taps = oracle.sinc_m2_channelizer(25000.0, m, 9)
+    ch = ComplexPolyphaseChannelizerM2(taps, 25000 * m, m)
+    ch.setSampleFormat(fmt)
+    got = np.concatenate([ch.receive(raw[:10000]), ch.receive(raw[10000:])])
+    ref = ComplexPolyphaseChannelizerM2(taps, 25000 * m, m).receive(want_f)       # same kernels on converted floats
+    assert np.array_equal(got, ref)
+    assert sg.rel_rms(got, oracle.Channelizer(taps, m).receive(want_f, mode="f64")) < TOL
