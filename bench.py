@@ -342,6 +342,8 @@ class GpuWorkload:
                                     max_samples_per_call=self.n_blocks, device=local_rank)
             self.bank.setStream(self.stream.cuda_stream)
             self.pipeline = Pipeline(self.chan, self.bank)
+            self.chunks = int(os.environ.get("SDRGPU_BENCH_CHUNKS", "8"))
+            self.pipeline.setChunks(self.chunks)
             self.sym_stride = self.n_blocks // 8 + 64          # > 4800/50000 symbols per sample
             self.sym_dev = torch.zeros((m, self.sym_stride), dtype=torch.uint8, device=dev)
             self.cnt_dev = torch.zeros(m, dtype=torch.int32, device=dev)
@@ -405,6 +407,7 @@ class GpuWorkload:
         self.chan.enableTiming(True)
         if self.pipeline is not None:
             self.bank.enableTiming(True)
+            self.pipeline.setChunks(1)        # one full-size launch per kernel, so that each time is a whole step's
         rows = []
         for _ in range(steps):
             self.step_device()
@@ -416,6 +419,7 @@ class GpuWorkload:
         self.chan.enableTiming(False)
         if self.pipeline is not None:
             self.bank.enableTiming(False)
+            self.pipeline.setChunks(self.chunks)
         return {k: statistics.mean(r[k] for r in rows) for k in rows[0]}
 
 

@@ -232,6 +232,9 @@ sdrgpu_status sdrgpu_bank_last_kernel_ms(sdrgpu_bank *b, float *ms2);
 typedef struct sdrgpu_pipeline sdrgpu_pipeline;
 sdrgpu_status sdrgpu_pipeline_create(sdrgpu_pipeline **p, sdrgpu_channelizer *chan, sdrgpu_bank *bank);
 sdrgpu_status sdrgpu_pipeline_destroy(sdrgpu_pipeline *p); /* does not destroy chan / bank */
+/* a process call is cut into `chunks` time chunks (default 8; 1 = single pass) so that copies, channelizer / filter
+ * kernels and the latency-bound demodulator of successive chunks overlap; the results do not depend on it */
+sdrgpu_status sdrgpu_pipeline_set_chunks(sdrgpu_pipeline *p, int chunks);
 sdrgpu_status sdrgpu_pipeline_process(sdrgpu_pipeline *p, const void *iq, int n_floats, int in_mem,
                                       uint8_t *symbols, int symbol_stride, float *demod,
                                       long long demod_stride_floats, int *counts, int out_mem);

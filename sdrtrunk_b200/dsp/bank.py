@@ -181,6 +181,9 @@ class Pipeline:
         native.check(native.lib().sdrgpu_pipeline_create(C.byref(self._h), channelizer._h, bank._h))
         self._pending = 0
 
+    def setChunks(self, chunks):
+        native.check(native.lib().sdrgpu_pipeline_set_chunks(self._h, int(chunks)))
+
     def process(self, samples, samples_mem=native.HOST, n_floats=None):
         """samples: float32 interleaved tuner I/Q.  Returns per-channel dibit arrays (DQPSK) or demod floats."""
         L = native.lib()
