@@ -192,7 +192,13 @@ typedef struct {
 /* presets of the reference's decoder front-ends (chain order + constants):
  * P25P1DecoderC4FM.java:62-93, P25P1DecoderLSM.java:67-106, P25P2DecoderHDQPSK.java:62-110,
  * NBFMDecoder.java:55-62,262-349 */
-enum { SDRGPU_PRESET_P25_C4FM = 0, SDRGPU_PRESET_P25_LSM = 1, SDRGPU_PRESET_P25_HDQPSK = 2, SDRGPU_PRESET_NBFM = 3 };
+enum {
+    SDRGPU_PRESET_P25_C4FM = 0,
+    SDRGPU_PRESET_P25_LSM = 1,
+    SDRGPU_PRESET_P25_HDQPSK = 2,
+    SDRGPU_PRESET_NBFM = 3,
+    SDRGPU_PRESET_DMR = 4 /* J/module/decode/dmr/DMRDecoder.java:58-131: FIR -> AGC -> decision-directed, BW_300, gain 0.4 */
+};
 sdrgpu_status sdrgpu_bank_config_preset(sdrgpu_bank_config *cfg, int preset, int n_channels, double sample_rate,
                                         const float *fir_taps, int n_fir_taps, int max_samples_per_call);
 

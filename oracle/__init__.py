@@ -455,7 +455,7 @@ def pack_dibits(dibits):
     return out[:n]
 
 
-C4FM, LSM, HDQPSK = 0, 1, 2
+C4FM, LSM, HDQPSK, DMR = 0, 1, 2, 3
 
 
 class P25Chain:

@@ -321,6 +321,9 @@ orc_p25_chain *orc_p25_chain_create(int kind, double sample_rate, const float *f
         c->psk = orc_psk_create(ORC_PSK_DECISION_DIRECTED, sample_rate, 4800.0, 300.0, 0.3f);
     } else if (kind == 1) {
         c->psk = orc_psk_create(ORC_PSK_GARDNER, sample_rate, 4800.0, 200.0, 0.3f);
+    } else if (kind == 3) { /* DMRDecoder.java:58-131: FIR + AGC + DD, BW_300, gain .4, 4800 */
+        c->fir = orc_cfir_create(fir_taps, n_taps, 1.0f);
+        c->psk = orc_psk_create(ORC_PSK_DECISION_DIRECTED, sample_rate, 4800.0, 300.0, 0.4f);
     } else {
         c->fir = orc_cfir_create(fir_taps, n_taps, 1.0f);
         c->psk = orc_psk_create(ORC_PSK_GARDNER, sample_rate, 6000.0, 300.0, 0.1f);

@@ -175,7 +175,7 @@ int orc_pack_dibits(const uint8_t *dibits, int n, uint8_t *out);
 /* ---------------------------------------------------------------- whole chains (a18) used as CPU baseline */
 typedef struct orc_p25_chain orc_p25_chain;
 /* kind: 0 = C4FM (FIR + AGC + DD, BW300, gain .3, 4800), 1 = LSM (no FIR, AGC, Gardner BW200 .3, 4800),
- *       2 = HDQPSK (FIR + AGC + Gardner BW300 .1, 6000) */
+ *       2 = HDQPSK (FIR + AGC + Gardner BW300 .1, 6000), 3 = DMR (FIR + AGC + DD, BW300 .4, 4800) */
 orc_p25_chain *orc_p25_chain_create(int kind, double sample_rate, const float *fir_taps, int n_taps);
 void orc_p25_chain_destroy(orc_p25_chain *c);
 /* consumes whole 1024-complex-sample buffers only (the assembler framing); n_floats multiple of 2048 */

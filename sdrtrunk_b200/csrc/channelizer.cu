@@ -57,6 +57,7 @@ struct ChanParams {
     int M, T, half, H;
     int n_blocks, parity0;
     int n_sel, layout, gain_exact;
+    int prefetch_blocks; // L2 read-ahead distance of pfb2_kernel in blocks
     int identity;        // selection is every bin in order with one float-representable gain (gain_uniform)
     float gain_uniform;
     float inv_m;
@@ -287,13 +288,26 @@ struct YPad {
 
 template <int M, int R1, int R2, int NB, int TT, int NT>
 struct Pfb2Layout {
+    static_assert(NB == 8 || NB == 16, "the X swizzle is written for 8 or 16 blocks per tile");
     static constexpr int SV = M + 4;
-    static constexpr int LDX = NB + 1;
+    static constexpr int LDX = NB;    // X rows are unpadded; the column index is XOR-swizzled instead (x_index)
     static constexpr int R2P = YPad<R2>::value;
-    static constexpr int YB = R1 * R2P;
+    // Y rows of one block: padded so that a half-warp straddling two blocks (n2 = .. R2-1 of b, then n2 = 0 .. of b+1)
+    // lands on disjoint banks: stride == (even ceiling of R2) mod 16 float2
+    static constexpr int y_want = ((R2 % 16) + 1) & ~1;
+    static constexpr int y_base = R1 * R2P;
+    static constexpr int YB = y_base + ((y_want - y_base % 16) + 16) % 16;
     static constexpr int region0 = (NB * SV > M * LDX) ? NB * SV : M * LDX;
     static constexpr size_t smem_bytes = sizeof(float2) * (size_t)(region0 + NB * YB);
 };
+
+// X[k][b] with b XOR-swizzled by the row: step B writes a column (16 consecutive k, one b) and the store pass reads
+// rows (NB consecutive b of one or two k); both hit 16 distinct 8-byte banks per half-warp
+template <int NB>
+__device__ __forceinline__ int x_index(int k, int b)
+{
+    return k * NB + (b ^ ((k / (16 / NB)) & (NB - 1)));
+}
 
 template <int M, int NB, int TT, bool FAST>
 __device__ __forceinline__ void fb_thread(const ChanParams &p, const float2 *__restrict__ xin, int b0, int r, float2 *V,
@@ -315,16 +329,26 @@ __device__ __forceinline__ void fb_thread(const ChanParams &p, const float2 *__r
         for (int t = 0; t < TT; t++) {
             const int bl = pp + 2 * t;  // branch n: unit P = B - 2t
             if (bl >= 0 && bl < NB) {
+#ifdef SDRGPU_PFB_FMA
+                if (t == 0) accA[bl] = make_float2(__fmul_rn(x.x, hA[t]), __fmul_rn(x.y, hA[t]));
+                else accA[bl] = make_float2(__fmaf_rn(x.x, hA[t], accA[bl].x), __fmaf_rn(x.y, hA[t], accA[bl].y));
+#else
                 const float px = __fmul_rn(x.x, hA[t]), py = __fmul_rn(x.y, hA[t]);
                 // (the Java's 0.0f + product differs from the product only in the sign of a zero)
                 if (t == 0) accA[bl] = make_float2(px, py);
                 else accA[bl] = make_float2(__fadd_rn(accA[bl].x, px), __fadd_rn(accA[bl].y, py));
+#endif
             }
             const int bm = pp + 1 + 2 * t;  // branch n + M/2: unit P = B - 1 - 2t
             if (bm >= 0 && bm < NB) {
+#ifdef SDRGPU_PFB_FMA
+                if (t == 0) accB[bm] = make_float2(__fmul_rn(x.x, hB[t]), __fmul_rn(x.y, hB[t]));
+                else accB[bm] = make_float2(__fmaf_rn(x.x, hB[t], accB[bm].x), __fmaf_rn(x.y, hB[t], accB[bm].y));
+#else
                 const float px = __fmul_rn(x.x, hB[t]), py = __fmul_rn(x.y, hB[t]);
                 if (t == 0) accB[bm] = make_float2(px, py);
                 else accB[bm] = make_float2(__fadd_rn(accB[bm].x, px), __fadd_rn(accB[bm].y, py));
+#endif
             }
         }
     }
@@ -354,6 +378,14 @@ __global__ void __launch_bounds__(NT, MINB) pfb2_kernel(const ChanParams p)
         const long long first = (long long)b0 * half - p.state_len;                    // index into p.in of unit b0-(2T-1)
         const bool fast = first >= 0 && first + (long long)(NB + 2 * TT - 1) * half <= p.n_in;
         const float2 *xin = p.in + (fast ? first : 0);
+        {
+            // pull the new input of the tile that will run about a wave later into L2: the first touch of every input
+            // line otherwise costs the filter bank a DRAM round trip (+10 % measured)
+            const long long ahead = first + (long long)(2 * TT - 1 + (long long)p.prefetch_blocks) * half;
+            const int lines = NB * half * (int)sizeof(float2) / 128;
+            if (ahead >= 0 && ahead + (long long)NB * half <= p.n_in)
+                for (int i = tid; i < lines; i += NT) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.in + ahead + i * 16));
+        }
         if (fast) {
             for (int r = tid; r < half; r += NT) fb_thread<M, NB, TT, true>(p, xin, b0, r, V, SV);
         } else {
@@ -395,7 +427,7 @@ __global__ void __launch_bounds__(NT, MINB) pfb2_kernel(const ChanParams p)
         if (R2 & 1) a[R2 - 1] = Y[b * YB + k1 * R2P + R2 - 1];
         rfft::dft<R2>(a);
 #pragma unroll
-        for (int k2 = 0; k2 < R2; k2++) X[(k1 + R1 * k2) * LDX + b] = a[k2];
+        for (int k2 = 0; k2 < R2; k2++) X[x_index<NB>(k1 + R1 * k2, b)] = a[k2];
     }
     __syncthreads();
 
@@ -413,28 +445,20 @@ __global__ void __launch_bounds__(NT, MINB) pfb2_kernel(const ChanParams p)
             if (p.identity) {
                 // default selection: every bin in order, one float-representable gain
                 const float g = p.gain_uniform;
-                const float2 *xr = X + row0 * LDX + bl;
                 float *o = out + (size_t)row0 * p.out_stride;
                 const size_t ostep = (size_t)ROWS * p.out_stride;
-                constexpr int ITER = M / ROWS;          // whole passes; the remainder rows follow
 #pragma unroll 5
-                for (int it = 0; it < ITER; it++) {
-                    float2 v = xr[it * ROWS * LDX];
+                for (int c = row0; c < M; c += ROWS) {
+                    float2 v = X[x_index<NB>(c, bl)];
                     v.x = __fmul_rn(__fmul_rn(v.x, inv_m), g);
                     v.y = __fmul_rn(__fmul_rn(v.y, inv_m), g);
                     *reinterpret_cast<float2 *>(o) = v;
                     o += ostep;
                 }
-                if (ITER * ROWS + row0 < M) {
-                    float2 v = xr[ITER * ROWS * LDX];
-                    v.x = __fmul_rn(__fmul_rn(v.x, inv_m), g);
-                    v.y = __fmul_rn(__fmul_rn(v.y, inv_m), g);
-                    *reinterpret_cast<float2 *>(o) = v;
-                }
             } else if (p.gain_exact) {
                 for (int c = row0; c < p.n_sel; c += ROWS) {
                     const float g = __ldg(p.gain_f + c);
-                    float2 v = X[__ldg(p.sel + c) * LDX + bl];
+                    float2 v = X[x_index<NB>(__ldg(p.sel + c), bl)];
                     v.x = __fmul_rn(__fmul_rn(v.x, inv_m), g);
                     v.y = __fmul_rn(__fmul_rn(v.y, inv_m), g);
                     float *row = c < p.n_main ? p.out + (size_t)c * p.out_stride : p.out2 + (size_t)(c - p.n_main) * p.out2_stride;
@@ -443,7 +467,7 @@ __global__ void __launch_bounds__(NT, MINB) pfb2_kernel(const ChanParams p)
             } else {
                 for (int c = row0; c < p.n_sel; c += ROWS) {
                     const double g = __ldg(p.gain_d + c);
-                    float2 v = X[__ldg(p.sel + c) * LDX + bl];
+                    float2 v = X[x_index<NB>(__ldg(p.sel + c), bl)];
                     v.x = __double2float_rn(__dmul_rn((double)__fmul_rn(v.x, inv_m), g));
                     v.y = __double2float_rn(__dmul_rn((double)__fmul_rn(v.y, inv_m), g));
                     float *row = c < p.n_main ? p.out + (size_t)c * p.out_stride : p.out2 + (size_t)(c - p.n_main) * p.out2_stride;
@@ -457,7 +481,7 @@ __global__ void __launch_bounds__(NT, MINB) pfb2_kernel(const ChanParams p)
             const int k = i % M, bl = i / M;
             const int b = b0 + bl;
             if (b >= p.n_blocks) continue;
-            float2 v = X[k * LDX + bl];
+            float2 v = X[x_index<NB>(k, bl)];
             v.x = __fmul_rn(v.x, inv_m);
             v.y = __fmul_rn(v.y, inv_m);
             *reinterpret_cast<float2 *>(p.out + ((size_t)b * M + k) * 2) = v;
@@ -813,6 +837,8 @@ sdrgpu_status sdrgpu::chan_enqueue(sdrgpu_channelizer *h, const float2 *d_in, in
         p.layout = layout;
         p.gain_exact = h->gain_exact;
         p.identity = h->identity;
+        static const int pf_waves = getenv("SDRGPU_PFB_PREFETCH") ? atoi(getenv("SDRGPU_PFB_PREFETCH")) : 2;
+        p.prefetch_blocks = 148 * 8 * pf_waves;   // in quarter waves of 148 SMs x 4 CTAs x 8 blocks
         p.gain_uniform = h->gain_uniform;
         p.inv_m = 1.0f / (float)h->M;
         p.n_factors = (int)h->factors.size();

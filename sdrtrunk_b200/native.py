@@ -16,7 +16,7 @@ LAYOUT_RESULTS, LAYOUT_CHANNELS = 0, 1
 WINDOW_HAMMING, WINDOW_BLACKMAN = 0, 1
 DEMOD_NONE, DEMOD_FM, DEMOD_FM_SQUELCH, DEMOD_DQPSK_DECISION, DEMOD_DQPSK_GARDNER = 0, 1, 2, 3, 4
 FORMAT_F32, FORMAT_U8, FORMAT_S8, FORMAT_S16LE = 0, 1, 2, 3
-PRESET_P25_C4FM, PRESET_P25_LSM, PRESET_P25_HDQPSK, PRESET_NBFM = 0, 1, 2, 3
+PRESET_P25_C4FM, PRESET_P25_LSM, PRESET_P25_HDQPSK, PRESET_NBFM, PRESET_DMR = 0, 1, 2, 3, 4
 
 OK, ERR_INVALID_ARG, ERR_BAD_STATE, ERR_CUDA, ERR_OVERFLOW, ERR_DESIGN, ERR_NOMEM = range(7)
 

@@ -170,7 +170,7 @@ def _p25_signal(kind, rng, n, k):
     rate = 6000.0 if kind == "hdqpsk" else 4800.0
     dib = rng.integers(0, 4, int(n * rate / 50000) + 8)
     off, tp = rng.uniform(-200, 200), rng.uniform(0, 1)
-    if kind == "c4fm":
+    if kind in ("c4fm", "dmr"):      # DMR is 4FSK at 4800 sym/s as well
         z = sg.c4fm(dib, carrier_offset=off, timing_phase=tp, n_samples=n)
     else:
         z = sg.dqpsk(dib, symbol_rate=rate, carrier_offset=off, timing_phase=tp, n_samples=n)
@@ -188,14 +188,15 @@ def _score(decoded, truth, skip=300):
 def _preset(gpu, kind):
     return {"c4fm": (gpu.PRESET_P25_C4FM, oracle.C4FM, c4fm_taps()),
             "lsm": (gpu.PRESET_P25_LSM, oracle.LSM, None),
-            "hdqpsk": (gpu.PRESET_P25_HDQPSK, oracle.HDQPSK, hdqpsk_taps())}[kind]
+            "hdqpsk": (gpu.PRESET_P25_HDQPSK, oracle.HDQPSK, hdqpsk_taps()),
+            "dmr": (gpu.PRESET_DMR, oracle.DMR, c4fm_taps())}[kind]
 
 
-@pytest.mark.parametrize("kind", ["c4fm", "lsm", "hdqpsk"])
+@pytest.mark.parametrize("kind", ["c4fm", "lsm", "hdqpsk", "dmr"])
 def test_p25_bank_dibits_bit_exact(gpu, kind):
     from sdrtrunk_b200.dsp import Bank
     preset, okind, taps = _preset(gpu, kind)
-    rng = np.random.default_rng({"c4fm": 21, "lsm": 22, "hdqpsk": 23}[kind])
+    rng = np.random.default_rng({"c4fm": 21, "lsm": 22, "hdqpsk": 23, "dmr": 24}[kind])
     c, n = 12, 20 * 1024
     sigs = [_p25_signal(kind, rng, n, k) for k in range(c)]
     x = np.stack([s[0] for s in sigs])
