@@ -288,26 +288,21 @@ struct YPad {
 
 template <int M, int R1, int R2, int NB, int TT, int NT>
 struct Pfb2Layout {
-    static_assert(NB == 8 || NB == 16, "the X swizzle is written for 8 or 16 blocks per tile");
-    static constexpr int SV = M + 4;
-    static constexpr int LDX = NB;    // X rows are unpadded; the column index is XOR-swizzled instead (x_index)
-    static constexpr int R2P = YPad<R2>::value;
-    // Y rows of one block: padded so that a half-warp straddling two blocks (n2 = .. R2-1 of b, then n2 = 0 .. of b+1)
-    // lands on disjoint banks: stride == (even ceiling of R2) mod 16 float2
-    static constexpr int y_want = ((R2 % 16) + 1) & ~1;
+    static_assert(NB == 8 || NB == 16, "strides and thread mappings are chosen for 8 or 16 blocks per tile");
+    static constexpr int Mp = (M + 15) & ~15;
+    // NB == 8: steps A and B map lanes to (block fastest, then n2 / k1): 8 lanes of one n2 / k1 and their neighbour
+    // form a half-warp, so every per-block row stride == 2 (mod 16 float2) spreads a half-warp over all 16 banks --
+    // V reads, Y writes, Y LDS.128 reads (stride / 2 odd), X writes and the store pass's X reads are all conflict free.
+    // NB == 16 (small M): lanes run over n2 / k1 first; strides == 4 (mod 16) keep row-straddling half-warps apart.
+    static constexpr int SV = NB == 8 ? Mp + 2 : Mp + 4;      // V[b][n]
+    static constexpr int XS = NB == 8 ? Mp + 2 : Mp + 1;      // X[b][k]
+    static constexpr int R2P = YPad<R2>::value;               // Y[b][k1][R2P]
     static constexpr int y_base = R1 * R2P;
+    static constexpr int y_want = NB == 8 ? 2 : (((R2 % 16) + 1) & ~1);
     static constexpr int YB = y_base + ((y_want - y_base % 16) + 16) % 16;
-    static constexpr int region0 = (NB * SV > M * LDX) ? NB * SV : M * LDX;
+    static constexpr int region0 = (NB * SV > NB * XS) ? NB * SV : NB * XS;
     static constexpr size_t smem_bytes = sizeof(float2) * (size_t)(region0 + NB * YB);
 };
-
-// X[k][b] with b XOR-swizzled by the row: step B writes a column (16 consecutive k, one b) and the store pass reads
-// rows (NB consecutive b of one or two k); both hit 16 distinct 8-byte banks per half-warp
-template <int NB>
-__device__ __forceinline__ int x_index(int k, int b)
-{
-    return k * NB + (b ^ ((k / (16 / NB)) & (NB - 1)));
-}
 
 template <int M, int NB, int TT, bool FAST>
 __device__ __forceinline__ void fb_thread(const ChanParams &p, const float2 *__restrict__ xin, int b0, int r, float2 *V,
@@ -365,9 +360,9 @@ template <int M, int R1, int R2, int NB, int TT, int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB) pfb2_kernel(const ChanParams p)
 {
     using L = Pfb2Layout<M, R1, R2, NB, TT, NT>;
-    constexpr int half = M / 2, SV = L::SV, LDX = L::LDX, R2P = L::R2P, YB = L::YB;
+    constexpr int half = M / 2, SV = L::SV, XS = L::XS, R2P = L::R2P, YB = L::YB;
     extern __shared__ __align__(16) float2 smem[];
-    float2 *V = smem;                 // [NB][SV], later X [M][LDX]
+    float2 *V = smem;                 // [NB][SV], later X [NB][XS]
     float2 *Y = smem + L::region0;    // [NB][R1][R2P]
     const int tid = threadIdx.x;
     const int b0 = blockIdx.x * NB;
@@ -396,7 +391,7 @@ __global__ void __launch_bounds__(NT, MINB) pfb2_kernel(const ChanParams p)
 
     // ------------------------------------------------------------------ 2. step A: R1-point DFTs over n1
     for (int item = tid; item < NB * R2; item += NT) {
-        const int b = item / R2, n2 = item - b * R2;
+        const int b = NB == 8 ? (item & 7) : item / R2, n2 = NB == 8 ? (item >> 3) : item - b * R2;
         float2 a[R1];
         const float2 *v = V + b * SV + n2;
 #pragma unroll
@@ -415,7 +410,7 @@ __global__ void __launch_bounds__(NT, MINB) pfb2_kernel(const ChanParams p)
     // ------------------------------------------------------------------ 3. step B: R2-point DFTs over n2
     float2 *X = V;
     for (int item = tid; item < NB * R1; item += NT) {
-        const int b = item / R1, k1 = item - b * R1;
+        const int b = NB == 8 ? (item & 7) : item / R1, k1 = NB == 8 ? (item >> 3) : item - b * R1;
         float2 a[R2];
         const float4 *y = reinterpret_cast<const float4 *>(Y + b * YB + k1 * R2P);
 #pragma unroll
@@ -427,7 +422,9 @@ __global__ void __launch_bounds__(NT, MINB) pfb2_kernel(const ChanParams p)
         if (R2 & 1) a[R2 - 1] = Y[b * YB + k1 * R2P + R2 - 1];
         rfft::dft<R2>(a);
 #pragma unroll
-        for (int k2 = 0; k2 < R2; k2++) X[x_index<NB>(k1 + R1 * k2, b)] = a[k2];
+        float2 *xo = X + b * XS + k1;
+#pragma unroll
+        for (int k2 = 0; k2 < R2; k2++) xo[R1 * k2] = a[k2];
     }
     __syncthreads();
 
@@ -447,9 +444,10 @@ __global__ void __launch_bounds__(NT, MINB) pfb2_kernel(const ChanParams p)
                 const float g = p.gain_uniform;
                 float *o = out + (size_t)row0 * p.out_stride;
                 const size_t ostep = (size_t)ROWS * p.out_stride;
+                const float2 *xr = X + bl * XS;
 #pragma unroll 5
                 for (int c = row0; c < M; c += ROWS) {
-                    float2 v = X[x_index<NB>(c, bl)];
+                    float2 v = xr[c];
                     v.x = __fmul_rn(__fmul_rn(v.x, inv_m), g);
                     v.y = __fmul_rn(__fmul_rn(v.y, inv_m), g);
                     *reinterpret_cast<float2 *>(o) = v;
@@ -458,7 +456,7 @@ __global__ void __launch_bounds__(NT, MINB) pfb2_kernel(const ChanParams p)
             } else if (p.gain_exact) {
                 for (int c = row0; c < p.n_sel; c += ROWS) {
                     const float g = __ldg(p.gain_f + c);
-                    float2 v = X[x_index<NB>(__ldg(p.sel + c), bl)];
+                    float2 v = X[bl * XS + __ldg(p.sel + c)];
                     v.x = __fmul_rn(__fmul_rn(v.x, inv_m), g);
                     v.y = __fmul_rn(__fmul_rn(v.y, inv_m), g);
                     float *row = c < p.n_main ? p.out + (size_t)c * p.out_stride : p.out2 + (size_t)(c - p.n_main) * p.out2_stride;
@@ -467,7 +465,7 @@ __global__ void __launch_bounds__(NT, MINB) pfb2_kernel(const ChanParams p)
             } else {
                 for (int c = row0; c < p.n_sel; c += ROWS) {
                     const double g = __ldg(p.gain_d + c);
-                    float2 v = X[x_index<NB>(__ldg(p.sel + c), bl)];
+                    float2 v = X[bl * XS + __ldg(p.sel + c)];
                     v.x = __double2float_rn(__dmul_rn((double)__fmul_rn(v.x, inv_m), g));
                     v.y = __double2float_rn(__dmul_rn((double)__fmul_rn(v.y, inv_m), g));
                     float *row = c < p.n_main ? p.out + (size_t)c * p.out_stride : p.out2 + (size_t)(c - p.n_main) * p.out2_stride;
@@ -481,7 +479,7 @@ __global__ void __launch_bounds__(NT, MINB) pfb2_kernel(const ChanParams p)
             const int k = i % M, bl = i / M;
             const int b = b0 + bl;
             if (b >= p.n_blocks) continue;
-            float2 v = X[x_index<NB>(k, bl)];
+            float2 v = X[bl * XS + k];
             v.x = __fmul_rn(v.x, inv_m);
             v.y = __fmul_rn(v.y, inv_m);
             *reinterpret_cast<float2 *>(p.out + ((size_t)b * M + k) * 2) = v;
