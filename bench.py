@@ -42,6 +42,13 @@ WORKLOADS = {
     "c4fm": dict(fs=1e7, taps_per_channel=9, seconds=1.0, demod="c4fm",
                  desc="configs[2]: channelizer 10 MS/s -> 400 channels + 72-tap FIR + block AGC + DQPSK "
                       "decision-directed timing recovery (P25 Phase 1 C4FM) on all 400 channels, dibits out"),
+    # BASELINE.json configs[4], one GPU's share: one 20 MS/s tuner -> 800 channels (M = 800)
+    "channelizer_20m": dict(fs=2e7, taps_per_channel=9, seconds=1.0, demod=None,
+                            desc="configs[4] per-GPU share: polyphase channelizer 20 MS/s -> 800 x 25 kHz channels "
+                                 "(M=800, T=9), all bins kept, gain M, [channel][time] output"),
+    "c4fm_20m": dict(fs=2e7, taps_per_channel=9, seconds=1.0, demod="c4fm",
+                     desc="configs[4] per-GPU share: 20 MS/s tuner -> 800 channels + 72-tap FIR + AGC + C4FM DQPSK "
+                          "timing recovery on all 800 channels, dibits out"),
 }
 
 
@@ -326,7 +333,8 @@ class GpuWorkload:
         # synthetic tuner I/Q generated on the device, and its pinned host copy
         self.truth = None
         if cfg["demod"] == "c4fm":
-            self.x_dev, self.truth = synth_c4fm_wideband(torch, dev, m, self.n_blocks, seed=3 + 1000 * rank)
+            self.x_dev, self.truth = synth_c4fm_wideband(torch, dev, m, self.n_blocks, seed=3 + 1000 * rank,
+                                                         amplitude=8.0 / m)
         else:
             self.x_dev = synth_tones_wideband(torch, dev, m, n_complex, seed=2 + 1000 * rank)
         self.x_host = torch.empty(self.n_floats, dtype=torch.float32, pin_memory=True)
@@ -396,7 +404,7 @@ class GpuWorkload:
         self.step_host()
         cnt = self.cnt_host.numpy()
         out = {}
-        for c in (0, 57, 200, 399):
+        for c in (0, 57, self.m // 2, self.m - 1):
             dec = self.sym_host.numpy()[c, :cnt[c]]
             out[str(c)] = {"symbols": int(cnt[c]), "match_after_acquisition": round(dibit_match(dec, self.truth[c]), 4)}
         return out
@@ -505,7 +513,7 @@ def run_gpu(args, rank, world, local_rank):
             k_ms = r["kernels"]["pfb_ifft"]
             ach = alg / (k_ms * 1e-3) / 1e9
             return {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": load_traffic("pfb_ifft_kernel"), "kernel": "pfb_ifft_kernel", "kernel_ms": k_ms,
+                    "traffic": load_traffic("pfb2_kernel") if w.m == 400 else None, "kernel": "pfb2_kernel", "kernel_ms": k_ms,
                     "algorithmic_bytes_per_launch": alg, "peak_source": peak_src}
         # chain: report the serial timing-recovery kernel (latency bound) with the HBM bytes it moves, and the
         # FP32 view of the FIR that feeds it
