@@ -194,6 +194,7 @@ class Pipeline:
             in_ptr = native.ptr(samples)
         else:
             in_ptr = native.ptr(samples)
+            n_floats = int(n_floats)
         n = self.channelizer.blocksFor(n_floats)
         blocks = (self._pending + n) // bank.block_size
         n_out = blocks * (bank.block_size // max(bank.decimation, 1))

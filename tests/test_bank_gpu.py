@@ -356,3 +356,96 @@ def test_config1_nbfm_chain(gpu):
     assert np.max(np.abs(got - audio)) < 1e-5
     # it is the 1 kHz tone at +/-2.5 kHz deviation: peak angle per 25 kHz sample = 2 pi 2500 / 25000
     assert abs(np.max(got[1000:]) - 2 * np.pi * 2500 / 25000) < 2e-2
+
+
+# ------------------------------------------------------------------------------------------------ edge cases
+def test_empty_short_and_oversized_calls(gpu):
+    from sdrtrunk_b200.dsp import Bank
+    rng = np.random.default_rng(41)
+    taps = c4fm_taps()
+    bank = Bank.preset(gpu.PRESET_P25_C4FM, 2, 50000.0, taps, max_samples_per_call=2048)
+    assert [d.size for d in bank.process(np.zeros((2, 0), np.float32))] == [0, 0]          # empty buffer
+    x, _ = _p25_signal("c4fm", rng, 4096, 0)
+    x = np.stack([x, x])
+    a = bank.process(x[:, :2 * 1000])                                                       # < one assembler buffer
+    assert [d.size for d in a] == [0, 0]
+    b = bank.process(x[:, 2 * 1000:2 * 2048])                                               # completes two buffers
+    ref = oracle.P25Chain(oracle.C4FM, 50000.0, taps).receive(x[0, :2 * 2048])
+    assert np.array_equal(b[0], ref) and np.array_equal(b[1], ref)
+    with pytest.raises(gpu.OverflowError_):
+        bank.process(np.zeros((2, 2 * 4096), np.float32))                                   # > max_samples_per_call
+    with pytest.raises(gpu.IllegalArgumentException):
+        Bank(1, 50000.0, decimation=3)                                                      # DecimationFilterFactory.java:62-64
+    with pytest.raises(gpu.IllegalArgumentException):
+        Bank(1, 9000.0, demod=gpu.DEMOD_DQPSK_DECISION, symbol_rate=4800.0, pll_bandwidth=300.0,
+             sample_counter_gain=0.3)                                                       # sample rate <= 2 * symbol rate
+
+
+def test_pack_dibits_matches_oracle(gpu):
+    import ctypes as C
+    rng = np.random.default_rng(42)
+    for n in (0, 1, 3, 4, 5, 103):
+        d = rng.integers(0, 4, n).astype(np.uint8)
+        out = np.zeros(n // 4 + 1, np.uint8)
+        got = gpu.lib().sdrgpu_pack_dibits(d.ctypes.data_as(C.POINTER(C.c_uint8)), n, out.ctypes.data_as(C.POINTER(C.c_uint8)))
+        want = oracle.pack_dibits(d)
+        assert got == want.size and np.array_equal(out[:got], want)
+
+
+def test_pipeline_result_is_independent_of_chunking_and_memory_space(gpu):
+    """the time-chunked, stream-overlapped host path, the single pass and device-resident input give identical dibits"""
+    import ctypes as C
+    from sdrtrunk_b200.dsp import Bank, ComplexPolyphaseChannelizerM2, Pipeline
+    m, n_ch = 96, 16 * 1024
+    rng = np.random.default_rng(43)
+    bins = [2, 30, 77]
+    base = [sg.c4fm(rng.integers(0, 4, int(n_ch * 0.096) + 8), carrier_offset=rng.uniform(-200, 200),
+                    timing_phase=rng.uniform(0, 1), n_samples=n_ch, amplitude=0.05) for _ in bins]
+    x = sg.interleave(sg.multiplex(base, bins, m, n_ch) + sg.awgn(rng, n_ch * m // 2, 1e-3))
+    taps, fir = oracle.sinc_m2_channelizer(25000.0, m, 9), c4fm_taps()
+
+    def run(chunks, device_input):
+        chan = ComplexPolyphaseChannelizerM2(taps, 2400000, m, maxInputFloats=x.size)
+        chan.setChannels(bins)
+        pipe = Pipeline(chan, Bank.preset(gpu.PRESET_P25_C4FM, len(bins), 50000.0, fir, max_samples_per_call=n_ch))
+        pipe.setChunks(chunks)
+        if not device_input:
+            return pipe.process(x)
+        L = gpu.lib()
+        d_in = C.c_void_p()
+        gpu.check(L.sdrgpu_device_alloc(C.byref(d_in), x.nbytes))
+        gpu.check(L.sdrgpu_memcpy(d_in, gpu.ptr(x), x.nbytes, gpu.DEVICE, gpu.HOST))
+        out = pipe.process(d_in.value, gpu.DEVICE, x.size)
+        L.sdrgpu_device_free(d_in)
+        return out
+
+    ref = run(1, False)
+    assert all(r.size > 1500 for r in ref)
+    for chunks, dev in ((8, False), (3, False), (1, True), (8, True)):
+        got = run(chunks, dev)
+        assert all(np.array_equal(g, r) for g, r in zip(got, ref)), (chunks, dev)
+
+
+def test_config3_shape_all_400_channels(gpu):
+    """BASELINE configs[2] at full width: 10 MS/s, M = 400, every bin carries C4FM; all 400 channels through the fused
+    pipeline.  Every channel must decode its transmitted dibits (size-independent property), and a sample of channels
+    is bit-exact against the oracle chain fed the same channel I/Q."""
+    from sdrtrunk_b200.dsp import Bank, ComplexPolyphaseChannelizerM2, Pipeline
+    m, n_ch = 400, 8 * 1024
+    rng = np.random.default_rng(44)
+    dibs = [rng.integers(0, 4, int(n_ch * 0.096) + 8) for _ in range(m)]
+    base = [sg.c4fm(dibs[k], carrier_offset=rng.uniform(-200, 200), timing_phase=rng.uniform(0, 1), n_samples=n_ch,
+                    amplitude=0.02, phase0=rng.uniform(0, 6.28)) for k in range(m)]
+    x = sg.interleave(sg.multiplex(base, list(range(m)), m, n_ch) + sg.awgn(rng, n_ch * m // 2, 2e-3))
+    fir = c4fm_taps()
+    chan = ComplexPolyphaseChannelizerM2(1e7, 9, maxInputFloats=x.size)
+    pipe = Pipeline(chan, Bank.preset(gpu.PRESET_P25_C4FM, m, 50000.0, fir, max_samples_per_call=n_ch))
+    got = pipe.process(x)
+    assert len(got) == m
+    scores = np.array([_score(got[k], dibs[k], skip=200) for k in range(m)])
+    assert np.mean(scores > 0.97) > 0.95, np.sort(scores)[:10]
+    slow = [int(k) for k in np.nonzero(scores <= 0.97)[0]]     # slow acquisitions are the algorithm's, not the port's:
+    iq = ComplexPolyphaseChannelizerM2(1e7, 9, maxInputFloats=x.size).receiveChannels(x)
+    for k in [0, 1, 199, 200, 201, 399] + slow:                # ... they must match the oracle bit for bit as well
+        want = oracle.P25Chain(oracle.C4FM, 50000.0, fir).receive(iq[k])
+        assert np.array_equal(got[k], want), k
