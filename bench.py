@@ -310,6 +310,127 @@ def dibit_match(decoded, truth, skip=300):
             best = max(best, float(np.mean(decoded[lag + skip:lag + n] == truth[skip:n])))
     return best
 
+def synth_dqpsk_channels(torch, dev, n_channels, n, seed, symbol_rate=6000.0, fs=50000.0, beta=0.35, noise=0.03):
+    """channel-domain pi/4-DQPSK streams (raised-cosine shaped impulse train evaluated at the
+    non-integer 8.33 samples per symbol), carrier offset U(-200, 200) Hz and timing phase per channel, + AWGN."""
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    sps = fs / symbol_rate
+    n_sym = int(n / sps) + 16
+    out = torch.empty((n_channels, 2 * n), dtype=torch.float32, device=dev)
+    truth = torch.empty((n_channels, n_sym), dtype=torch.uint8)
+    levels = torch.tensor([1.0, 3.0, -1.0, -3.0], device=dev, dtype=torch.float64)
+    idx = torch.arange(n, device=dev, dtype=torch.float64).unsqueeze(0)
+    for lo in range(0, n_channels, 256):
+        hi = min(n_channels, lo + 256)
+        c = hi - lo
+        dib = torch.randint(0, 4, (c, n_sym), device=dev, generator=g)
+        truth[lo:hi] = dib.to(torch.uint8).cpu()
+        sym = torch.polar(torch.ones((c, n_sym), device=dev, dtype=torch.float64),
+                          torch.cumsum(levels[dib] * (np.pi / 4.0), dim=1))
+        off = (torch.rand(c, 1, device=dev, generator=g, dtype=torch.float64) - 0.5) * 400.0
+        tph = torch.rand(c, 1, device=dev, generator=g, dtype=torch.float64)
+        t = idx / sps - tph
+        k0 = torch.floor(t).long()
+        z = torch.zeros((c, n), dtype=torch.complex128, device=dev)
+        for dk in range(-6, 8):
+            k = k0 + dk
+            valid = (k >= 0) & (k < n_sym)
+            u = t - k
+            den = 1.0 - (2 * beta * u) ** 2
+            pulse = torch.where(den.abs() < 1e-9, torch.full_like(u, (np.pi / 4) * np.sinc(1 / (2 * beta))),
+                                torch.sinc(u) * torch.cos(np.pi * beta * u) / den)
+            z += torch.where(valid, torch.gather(sym, 1, k.clamp(0, n_sym - 1)) * pulse, torch.zeros_like(z))
+        z = z * torch.polar(torch.ones_like(idx), 2 * np.pi * off * idx / fs)
+        zr = torch.view_as_real(z.to(torch.complex64)).reshape(c, 2 * n)
+        out[lo:hi] = zr + noise * torch.randn(zr.shape, device=dev, generator=g, dtype=torch.float32)
+        del sym, t, k0, z, zr
+    return out, truth.numpy()
+
+
+def run_config4(args, rank, world, local_rank):
+    """BASELINE configs[3]: P25 Phase 2 HDQPSK on >= 1000 channel-domain streams (no channelizer): 154-tap FIR -> AGC ->
+    Gardner timing recovery, one warp per channel.  Channels are sharded over the ranks (level 3 of SURVEY 8e)."""
+    import scipy.signal as ss
+    import torch
+    import torch.distributed as dist
+    from sdrtrunk_b200 import native
+    from sdrtrunk_b200.dsp import Bank
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    native.init(local_rank)
+    L = native.lib()
+    dev = torch.device("cuda", local_rank)
+    channels, n = 4096, 24 * 1024                         # per GPU; 0.49 s of signal per step
+    fir = ss.remez(154, [0, 6500, 7200, 25000], [1, 0], fs=50000).astype(np.float32)
+    x, truth = synth_dqpsk_channels(torch, dev, channels, n, seed=4 + 1000 * rank)
+    bank = Bank.preset(native.PRESET_P25_HDQPSK, channels, 50000.0, fir, max_samples_per_call=n, device=local_rank)
+    stream = torch.cuda.Stream(device=dev)
+    bank.setStream(stream.cuda_stream)
+    stride = n // 7 + 64
+    sym = torch.zeros((channels, stride), dtype=torch.uint8, device=dev)
+    cnt = torch.zeros(channels, dtype=torch.int32, device=dev)
+
+    def step():
+        native.check(L.sdrgpu_bank_process(bank._h, C.c_void_p(x.data_ptr()), 2 * n, n, native.DEVICE,
+                                           C.c_void_p(sym.data_ptr()), stride, None, 0, C.c_void_p(cnt.data_ptr()),
+                                           native.DEVICE))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    step()
+    barrier()
+    first = sym.cpu().numpy()
+    counts = cnt.cpu().numpy()
+    sanity = {str(c): round(dibit_match(first[c, :counts[c]], truth[c], skip=300), 4) for c in (0, 1000, 4095)}
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = L.sdrgpu_launch_count()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    barrier()
+    launches = L.sdrgpu_launch_count() - launches0
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        tt = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = tt.item()
+    bank.enableTiming(True)
+    step()
+    k_filter, k_demod = bank.lastKernelMs()
+    if rank == 0:
+        ms_step = ms / args.steps
+        total = channels * n * world
+        peak, peak_src = load_peaks()
+        alg = 8.0 * channels * n + channels * n * 6000.0 / 50000.0
+        line = {"metric": METRIC, "value": total / (ms_step * 1e-3) / 1e6, "unit": UNIT, "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "configs[3]: P25 Phase 2 HDQPSK, %d channel-domain streams per GPU at 50 kHz "
+                                       "(channel samples, not tuner samples): 154-tap FIR + AGC + Gardner DQPSK "
+                                       "timing recovery, one warp per channel" % channels,
+                           "channels_per_gpu": channels, "samples_per_channel_per_step": n,
+                           "sharding": "channel rows per GPU, no collective"},
+                "realtime_channels": channels * world * (n / 50000.0) / (ms_step * 1e-3),
+                "gpu_launches": launches, "decode_sanity": sanity,
+                "kernels_ms": {"fir_agc": k_filter, "psk": k_demod},
+                "roofline": {"bound": "hbm", "achieved": alg / (k_demod * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                             "frac": alg / (k_demod * 1e-3) / 1e9 / peak, "traffic": None, "kernel": "psk_kernel<gardner>",
+                             "kernel_ms": k_demod, "algorithmic_bytes_per_launch": alg, "peak_source": peak_src,
+                             "note": "latency bound: one warp per channel"}}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 # ---------------------------------------------------------------------------------------------- GPU arm
 class GpuWorkload:
     """One workload's device state: synthetic input in HBM + pinned host copy, channelizer (+ bank + pipeline)."""
@@ -590,7 +711,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="channelizer", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="channelizer", choices=sorted(WORKLOADS) + ["hdqpsk_4096"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary configs[2] chain measurement")
     ap.add_argument("--device-only", action="store_true",
@@ -604,6 +725,9 @@ def main():
         return
     if args.warmup < 3:
         args.warmup = 3
+    if args.workload == "hdqpsk_4096":
+        run_config4(args, rank, world, local_rank)
+        return
     run_gpu(args, rank, world, local_rank)
 
 
