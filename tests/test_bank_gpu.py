@@ -253,12 +253,14 @@ def test_psk_drop_in_classes(gpu):
     assert seen == want
 
 
-def test_many_channels_one_warp_each(gpu):
+@pytest.mark.parametrize("c", [1024, 3072])
+def test_many_channels(gpu, c):
     """BASELINE config 4 shape: >= 1000 channel-domain streams; every channel gets the same input so that one
-    oracle run checks all 1024 warps."""
+    oracle run checks all of them.  1024 channels run one warp per channel (psk_kernel), 3072 one thread per channel
+    (psk_wide_kernel)."""
     from sdrtrunk_b200.dsp import Bank
     rng = np.random.default_rng(8)
-    c, n = 1024, 4 * 1024
+    n = 4 * 1024
     sig, _ = _p25_signal("hdqpsk", rng, n, 0)
     alt, _ = _p25_signal("hdqpsk", rng, n, 1)
     x = np.tile(sig, (c, 1))
