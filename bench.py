@@ -220,7 +220,7 @@ def run_reference(args, rank, world):
     chain = CpuChain(args.workload, cores)
     chain.run(1, 1)
     single_s, _ = chain.run(1, 1)
-    reps = max(1, int(1.0 / max(single_s * 1.3, 1e-3)))     # ~1-2 s per step
+    reps = max(1, int(2.5 / max(single_s * 1.3, 1e-3)))     # ~2.5-3 s per step: thread start / join stays < 1 %
     for _ in range(args.warmup):
         chain.run(reps)
     dt, total = 0.0, 0
