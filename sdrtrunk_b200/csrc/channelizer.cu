@@ -1036,7 +1036,9 @@ sdrgpu_status sdrgpu_chan_create(sdrgpu_channelizer **out, const float *taps, in
 sdrgpu_status sdrgpu_chan_destroy(sdrgpu_channelizer *h)
 {
     if (!h) return SDRGPU_OK;
-    if (h->stream) cudaStreamSynchronize(h->stream);
+    // a caller-owned stream may already be gone: never touch it here, wait for the device instead
+    if (h->stream && h->stream != h->own_stream) cudaDeviceSynchronize();
+    else if (h->own_stream) cudaStreamSynchronize(h->own_stream);
     cudaFree(h->d_taps);
     cudaFree(h->d_tw);
     cudaFree(h->d_tw2);
