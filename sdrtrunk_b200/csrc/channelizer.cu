@@ -421,7 +421,6 @@ __global__ void __launch_bounds__(NT, MINB) pfb2_kernel(const ChanParams p)
         }
         if (R2 & 1) a[R2 - 1] = Y[b * YB + k1 * R2P + R2 - 1];
         rfft::dft<R2>(a);
-#pragma unroll
         float2 *xo = X + b * XS + k1;
 #pragma unroll
         for (int k2 = 0; k2 < R2; k2++) xo[R1 * k2] = a[k2];
@@ -848,9 +847,7 @@ sdrgpu_status sdrgpu::chan_enqueue(sdrgpu_channelizer *h, const float2 *d_in, in
         h->timer.begin(h->stream);
         sdrgpu_status st;
         // tile sizes measured on B200 (profiles/): M = 400 runs best as 8-block tiles, 200 threads, 4 CTAs per SM
-        static const int variant = getenv("SDRGPU_PFB_VARIANT") ? atoi(getenv("SDRGPU_PFB_VARIANT")) : 0;
-        if (h->fast_r1 && h->M == 400 && variant == 1) st = launch_pfb2<400, 20, 20, 16, 9, 320, 2>(h, p);
-        else if (h->fast_r1 && h->M == 400) st = launch_pfb2<400, 20, 20, 8, 9, 200, 4>(h, p);
+        if (h->fast_r1 && h->M == 400) st = launch_pfb2<400, 20, 20, 8, 9, 200, 4>(h, p);
         else if (h->fast_r1 && h->M == 800) st = launch_pfb2<800, 32, 25, 8, 9, 256, 2>(h, p);
         else if (h->fast_r1 && h->M == 96) st = launch_pfb2<96, 8, 12, 16, 9, 192, 2>(h, p);
         else if (h->NB == 16) st = (h->T == 9) ? launch_pfb<16, 9>(h, p, grid) : launch_pfb<16, 0>(h, p, grid);
