@@ -409,6 +409,10 @@ __global__ void __launch_bounds__(NT, MINB) pfb2_kernel(const ChanParams p)
 
     // ------------------------------------------------------------------ 3. step B: R2-point DFTs over n2
     float2 *X = V;
+    // Default selection (every bin in order, one float-representable gain) with block-fastest lanes: the 8 lanes that
+    // hold one bin's 8 consecutive samples write them straight to that channel's row (64 contiguous bytes), so the
+    // X transpose, its barrier and the store pass are skipped.
+    const bool direct = NB == 8 && p.identity && p.layout == SDRGPU_LAYOUT_CHANNELS;
     for (int item = tid; item < NB * R1; item += NT) {
         const int b = NB == 8 ? (item & 7) : item / R1, k1 = NB == 8 ? (item >> 3) : item - b * R1;
         float2 a[R2];
@@ -421,10 +425,28 @@ __global__ void __launch_bounds__(NT, MINB) pfb2_kernel(const ChanParams p)
         }
         if (R2 & 1) a[R2 - 1] = Y[b * YB + k1 * R2P + R2 - 1];
         rfft::dft<R2>(a);
-        float2 *xo = X + b * XS + k1;
+        if (direct) {
+            if (b0 + b < p.n_blocks) {
+                // FloatFFT_1D.complexInverse(a, true): a[i] *= 1.0f / n; then applyGain
+                const float inv = p.inv_m, g = p.gain_uniform;
+                float *o = p.out + (size_t)k1 * p.out_stride + 2 * (size_t)(b0 + b);
+                const size_t ostep = (size_t)R1 * p.out_stride;
 #pragma unroll
-        for (int k2 = 0; k2 < R2; k2++) xo[R1 * k2] = a[k2];
+                for (int k2 = 0; k2 < R2; k2++) {
+                    float2 v = a[k2];
+                    v.x = __fmul_rn(__fmul_rn(v.x, inv), g);
+                    v.y = __fmul_rn(__fmul_rn(v.y, inv), g);
+                    *reinterpret_cast<float2 *>(o) = v;
+                    o += ostep;
+                }
+            }
+        } else {
+            float2 *xo = X + b * XS + k1;
+#pragma unroll
+            for (int k2 = 0; k2 < R2; k2++) xo[R1 * k2] = a[k2];
+        }
     }
+    if (direct) return;
     __syncthreads();
 
     // ------------------------------------------------------------------ 4. scale + store
