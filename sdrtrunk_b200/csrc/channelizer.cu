@@ -872,6 +872,14 @@ sdrgpu_status sdrgpu::chan_enqueue(sdrgpu_channelizer *h, const float2 *d_in, in
         if (h->fast_r1 && h->M == 400) st = launch_pfb2<400, 20, 20, 8, 9, 200, 4>(h, p);
         else if (h->fast_r1 && h->M == 800) st = launch_pfb2<800, 32, 25, 8, 9, 256, 2>(h, p);
         else if (h->fast_r1 && h->M == 96) st = launch_pfb2<96, 8, 12, 16, 9, 192, 2>(h, p);
+        else if (h->fast_r1 && h->M == 640) st = launch_pfb2<640, 32, 20, 8, 9, 320, 2>(h, p);
+        else if (h->fast_r1 && h->M == 320) st = launch_pfb2<320, 16, 20, 8, 9, 160, 4>(h, p);
+        else if (h->fast_r1 && h->M == 240) st = launch_pfb2<240, 12, 20, 8, 9, 160, 4>(h, p);
+        else if (h->fast_r1 && h->M == 200) st = launch_pfb2<200, 10, 20, 8, 9, 160, 4>(h, p);
+        else if (h->fast_r1 && h->M == 160) st = launch_pfb2<160, 8, 20, 8, 9, 160, 4>(h, p);
+        else if (h->fast_r1 && h->M == 120) st = launch_pfb2<120, 10, 12, 16, 9, 192, 2>(h, p);
+        else if (h->fast_r1 && h->M == 100) st = launch_pfb2<100, 10, 10, 16, 9, 160, 2>(h, p);
+        else if (h->fast_r1 && h->M == 80) st = launch_pfb2<80, 8, 10, 16, 9, 160, 2>(h, p);
         else if (h->NB == 16) st = (h->T == 9) ? launch_pfb<16, 9>(h, p, grid) : launch_pfb<16, 0>(h, p, grid);
         else st = (h->T == 9) ? launch_pfb<8, 9>(h, p, grid) : launch_pfb<8, 0>(h, p, grid);
         h->timer.end(h->stream);
@@ -1024,9 +1032,13 @@ sdrgpu_status sdrgpu_chan_create(sdrgpu_channelizer **out, const float *taps, in
     CHK(cudaMemcpy(h->d_tw, tw.data(), sizeof(float2) * (size_t)M, cudaMemcpyHostToDevice));
     // fast path (pfb2_kernel) for the channel counts of the common tuner rates with the reference's 9 taps per channel
     if (h->T == 9) {
-        if (M == 400) { h->fast_r1 = 20; h->fast_r2 = 20; }
-        else if (M == 800) { h->fast_r1 = 32; h->fast_r2 = 25; }
-        else if (M == 96) { h->fast_r1 = 8; h->fast_r2 = 12; }
+        // channel counts of the common tuner rates (25 kHz channels): 2 / 2.4 / 2.5 / 3 / 4 / 5 / 6 / 8 / 10 / 16 / 20 MS/s
+        static const int fast[][3] = {{400, 20, 20}, {800, 32, 25}, {96, 8, 12}, {640, 32, 20}, {320, 16, 20}, {240, 12, 20}, {200, 10, 20}, {160, 8, 20}, {120, 10, 12}, {100, 10, 10}, {80, 8, 10}};
+        for (const auto &f : fast)
+            if (M == f[0]) {
+                h->fast_r1 = f[1];
+                h->fast_r2 = f[2];
+            }
     }
     if (h->fast_r1) {
         std::vector<float2> tw2((size_t)M);

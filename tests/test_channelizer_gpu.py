@@ -25,7 +25,7 @@ def _signal(rng, n, m):
     return sg.interleave(z)
 
 
-@pytest.mark.parametrize("m", [96, 400, 800, 114, 70, 2])
+@pytest.mark.parametrize("m", [96, 400, 800, 114, 70, 2, 80, 100, 120, 160, 200, 240, 320, 640])
 def test_results_layout_matches_oracle(gpu, m):
     from sdrtrunk_b200.dsp import ComplexPolyphaseChannelizerM2
     rng = np.random.default_rng(m)
@@ -42,7 +42,7 @@ def test_results_layout_matches_oracle(gpu, m):
         assert sg.rel_rms(got[:, 2 * k:2 * k + 2], want[:, 2 * k:2 * k + 2]) < TOL
 
 
-@pytest.mark.parametrize("m", [96, 400])
+@pytest.mark.parametrize("m", [96, 400, 100, 320, 640])
 def test_channel_layout_matches_oracle_output_processor(gpu, m):
     from sdrtrunk_b200.dsp import ComplexPolyphaseChannelizerM2
     rng = np.random.default_rng(100 + m)
