@@ -1270,9 +1270,13 @@ sdrgpu_status sdrgpu_chan_process(sdrgpu_channelizer *h, const void *iq, int n_f
     int chunk = (n_in + 7) / 8;
     chunk = (chunk + tile - 1) / tile * tile;
     if (chunk < tile) chunk = tile;
+    // the first two chunks are a quarter of the rest: the D2H stream (the bottleneck) starts sooner
+    int small = (chunk / 4 + tile - 1) / tile * tile;
+    if (small < tile) small = tile;
     int done_in = 0, done_blocks = 0, ci = 0;
     while (done_in < n_in || (n_in == 0 && ci == 0)) {
-        const int n = (n_in - done_in < chunk) ? n_in - done_in : chunk;
+        const int want = ci < 2 ? small : chunk;
+        const int n = (n_in - done_in < want) ? n_in - done_in : want;
         const float2 *src_dev = nullptr;
         cudaEvent_t ev_in = h->events[(2 * ci) % kMaxEvents], ev_k = h->events[(2 * ci + 1) % kMaxEvents];
         if (in_mem == SDRGPU_HOST && n > 0) {
