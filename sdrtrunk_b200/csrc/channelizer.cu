@@ -268,17 +268,18 @@ __global__ void __launch_bounds__(kThreads) pfb_ifft_kernel(const ChanParams p)
 
 // ---------------------------------------------------------------------------------------------------------------
 // pfb2_kernel: the fast path for channel counts that split as M = R1 * R2 with register-sized factors
-// (400 = 20 x 20, 800 = 32 x 25, 96 = 8 x 12).  One CTA per tile of NB consecutive blocks:
+// (400 = 20 x 20, 800 = 32 x 25, 96 = 8 x 12, ... see sdrgpu_chan_create).  One CTA per tile of NB consecutive blocks:
+//   0. L2 read-ahead of the input the tile one wave later will need (its first touch is otherwise a DRAM round trip)
 //   1. filter bank (as above: thread <-> input offset r, taps in registers, NB blocks of two branches accumulated
 //      in registers, products rounded and added in tap order like the Java)         -> V[b][n]         (shared)
 //   2. step A: thread (b, n2) runs an R1-point DFT over n1 of V[b][R2 n1 + n2] in registers, multiplies by
 //      W_M^{n2 k1}                                                                  -> Y[b][k1][n2]    (shared)
-//   3. step B: thread (b, k1) runs an R2-point DFT over n2 in registers: bin k1 + R1 k2 -> X[k][b]     (shared)
-//   4. per-channel rows of NB consecutive samples (one 128-byte line for NB = 16) -> HBM, scaled by 1/M and the gain
-// Shared-memory traffic is 6 passes over the tile instead of 10 for the radix-4/5 Stockham version, and the index
-// arithmetic is compile-time.  Row strides: V rows M + 4 (== 4 mod 16 float2: the two half-warps of a 64-bit access
-// that straddle two rows hit disjoint banks), Y rows padded to an odd number of 16-byte slots (conflict-free
-// LDS.128), X rows NB + 1.
+//   3. step B: thread (b, k1) runs an R2-point DFT over n2 in registers: bin k1 + R1 k2.  With the default selection
+//      (every bin, one gain) and NB = 8 the 8 lanes holding one bin's 8 consecutive samples scale and write them
+//      straight to the channel's row (64 contiguous bytes) -- done.  Otherwise                -> X[b][k] (shared)
+//   4. (general selection) rows of NB consecutive samples per selected channel -> HBM, scaled by 1/M and the gain
+// Shared-memory traffic is 4 passes over the tile (6 with step 4) instead of 10 for the radix-4/5 Stockham version,
+// all bank-conflict free (Pfb2Layout), and the index arithmetic is compile-time.
 // ---------------------------------------------------------------------------------------------------------------
 template <int R2>
 struct YPad {
