@@ -64,6 +64,8 @@ struct ChanParams {
     int n_factors;
     int factors[kMaxFactors];
     unsigned magic_s[kMaxFactors];  // ceil(2^32 / s) for the stride of each pass
+    float2 *next_state;  // pfb2_kernel only: one CTA also writes the next call's history (else save_state_kernel)
+    int next_len, consumed;
 };
 
 __device__ __forceinline__ float2 load_x(const ChanParams &p, int unit, int r)
@@ -367,6 +369,18 @@ __global__ void __launch_bounds__(NT, MINB) pfb2_kernel(const ChanParams p)
     float2 *Y = smem + L::region0;    // [NB][R1][R2P]
     const int tid = threadIdx.x;
     const int b0 = blockIdx.x * NB;
+
+    // the history the next call starts from, next_state[i] = [state | in][consumed + i]: a few KB copied by one CTA of
+    // the middle of the grid into the other half of the state ping-pong (a separate launch costs 3 % of the step)
+    if (p.next_state != nullptr && blockIdx.x == (gridDim.x >> 1)) {
+        for (int i = tid; i < p.next_len; i += NT) {
+            const int idx = p.consumed + i;
+            float2 v = make_float2(0.0f, 0.0f);
+            if (idx < p.state_len) v = p.state[idx];
+            else if (idx - p.state_len < p.n_in) v = p.in[idx - p.state_len];
+            p.next_state[i] = v;
+        }
+    }
 
     // ------------------------------------------------------------------ 1. filter bank
     {
@@ -830,6 +844,11 @@ sdrgpu_status sdrgpu::chan_enqueue(sdrgpu_channelizer *h, const float2 *d_in, in
     if (n_blocks_out) *n_blocks_out = n_blocks;
     const float2 *state = h->d_state[h->cur_state];
     const int state_len = h->H + h->leftover;
+    const int consumed = n_blocks * h->half;
+    const int new_leftover = total - consumed;
+    const int new_len = h->H + new_leftover;
+    float2 *next = h->d_state[h->cur_state ^ 1];
+    bool state_saved = false;
     if (n_blocks > 0) {
         ChanParams p{};
         p.state = state;
@@ -867,6 +886,12 @@ sdrgpu_status sdrgpu::chan_enqueue(sdrgpu_channelizer *h, const float2 *d_in, in
             p.magic_s[i] = h->magic[i];
         }
         const int grid = (n_blocks + h->NB - 1) / h->NB;
+        if (h->fast_r1 && n_in > 0) {
+            p.next_state = next;
+            p.next_len = new_len;
+            p.consumed = consumed;
+            state_saved = true;
+        }
         h->timer.begin(h->stream);
         sdrgpu_status st;
         // tile sizes measured on B200 (profiles/): M = 400 runs best as 8-block tiles, 200 threads, 4 CTAs per SM
@@ -893,16 +918,14 @@ sdrgpu_status sdrgpu::chan_enqueue(sdrgpu_channelizer *h, const float2 *d_in, in
         }
     }
     // carry the history + leftover over to the next call
-    const int consumed = n_blocks * h->half;
-    const int new_leftover = total - consumed;
-    const int new_len = h->H + new_leftover;
-    float2 *next = h->d_state[h->cur_state ^ 1];
     if (n_in > 0) {
-        int grid = (new_len + 255) / 256;
-        if (grid > 1024) grid = 1024;
-        save_state_kernel<<<grid, 256, 0, h->stream>>>(state, state_len, d_in, n_in, consumed, next, new_len);
-        count_launch();
-        SDRGPU_CUDA(cudaGetLastError());
+        if (!state_saved) {
+            int grid = (new_len + 255) / 256;
+            if (grid > 1024) grid = 1024;
+            save_state_kernel<<<grid, 256, 0, h->stream>>>(state, state_len, d_in, n_in, consumed, next, new_len);
+            count_launch();
+            SDRGPU_CUDA(cudaGetLastError());
+        }
         h->cur_state ^= 1;
     }
     h->leftover = new_leftover;
