@@ -594,12 +594,21 @@ def measure(w, args, world, dist, barrier):
                   "d2h_bytes_per_step": w.d2h, "ms_per_step": u8_ms,
                   "input": "unsigned 8-bit tuner samples (ByteSampleConverter format), converted on the device"}
     kernels = w.kernel_times(min(args.steps, 10))
+    with_sync = None
+    if w.pipeline is not None:
+        # section 8f #3: the same step with the P25 Phase 1 sync detector + PLL inversion feedback running in the
+        # demodulator kernel
+        w.bank.setSyncDetector(w.native.SYNC_P25_PHASE1)
+        ms_sync, _ = timed(w.step_device, args.steps, 3)
+        w.bank.setSyncDetector(w.native.SYNC_NONE)
+        with_sync = {"ms_per_step": ms_sync / args.steps,
+                     "value": w.n_complex * world / (ms_sync / args.steps * 1e-3) / 1e6, "unit": UNIT}
     ms_per_step = ms_dev / args.steps
     total = w.n_complex * world
     e2e_ms = max(ms_e2e_dev, wall_e2e) / args.steps
     return {"ms_per_step": ms_per_step, "value": total / (ms_per_step * 1e-3) / 1e6,
             "e2e_ms": e2e_ms, "e2e_value": total / (e2e_ms * 1e-3) / 1e6, "launches": launches, "kernels": kernels,
-            "sanity": sanity, "e2e_u8": e2e_u8}
+            "sanity": sanity, "e2e_u8": e2e_u8, "with_sync": with_sync}
 
 
 def run_gpu(args, rank, world, local_rank):
@@ -664,6 +673,7 @@ def run_gpu(args, rank, world, local_rank):
                  "e2e": {"value": r2["e2e_value"], "unit": UNIT, "h2d_bytes_per_step": w2.h2d,
                          "d2h_bytes_per_step": w2.d2h, "ms_per_step": r2["e2e_ms"]},
                  "e2e_u8_input": r2["e2e_u8"],
+                 "with_sync_detector": r2["with_sync"],
                  "gpu_launches": r2["launches"], "kernels_ms": r2["kernels"], "roofline": roofline_of(w2, r2),
                  "decode_sanity": r2["sanity"]}
         del w2
@@ -698,6 +708,8 @@ def run_gpu(args, rank, world, local_rank):
     }
     if r.get("sanity") is not None:
         line["decode_sanity"] = r["sanity"]
+    if r.get("with_sync") is not None:
+        line["with_sync_detector"] = r["with_sync"]
     if extra is not None:
         line["chain_c4fm"] = extra
     print(json.dumps(line))

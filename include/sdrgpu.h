@@ -222,6 +222,29 @@ sdrgpu_status sdrgpu_bank_process(sdrgpu_bank *b, const float *iq, long long in_
  * buffer boundary of that channel (host-driven sync feedback, SURVEY.md hard part 4) */
 sdrgpu_status sdrgpu_bank_correct_inversion(sdrgpu_bank *b, int channel, double radians);
 sdrgpu_status sdrgpu_bank_reset_pll(sdrgpu_bank *b, int channel);
+/* Sync-pattern detection and the PLL phase-inversion feedback it drives, on the device, per channel:
+ * P25P1SyncDetector (J/module/decode/p25/phase1/P25P1SyncDetector.java:37-168: MultiSyncPatternMatcher over 48 bits,
+ * SoftSyncDetector(P25_PHASE1_NORMAL, 4 bit errors), exact detectors for the 90 CW / 90 CCW / 180 degree rotated
+ * patterns that call IPhaseLockedLoop.correctInversion(+-2 pi 1200 / fs, 2 pi 2400 / fs)) behind the 33-dibit delay
+ * buffer of P25P1DataUnitDetector.java:41,106; or P25P2SyncDetector (40 bits, J/module/decode/p25/phase2/
+ * P25P2SyncDetector.java:40-160) behind the 160-dibit delay of P25P2SuperFrameDetector.java:66,159.  The correction
+ * is applied at exactly the symbol the reference applies it (after that symbol's CostasLoop.adjust), not at the next
+ * buffer boundary.  The detector is fed every dibit, as the reference's framers feed it while they search for sync
+ * (they pause it while a message is being assembled / fragment sync is held; that framing stays on the host).
+ * With a detector enabled every symbol byte is  dibit | event << 2 | bit_errors << 5 :
+ * the event the detector raised at that symbol (syncDetected / correctInversion / syncLost) and, for
+ * SDRGPU_SYNC_EVENT_SYNC, the number of bit errors passed to ISyncDetectListener.syncDetected.
+ * Enabling (or re-enabling) starts from a fresh detector on every channel. */
+enum { SDRGPU_SYNC_NONE = 0, SDRGPU_SYNC_P25_PHASE1 = 1, SDRGPU_SYNC_P25_PHASE2 = 2 };
+enum {
+    SDRGPU_SYNC_EVENT_NONE = 0,
+    SDRGPU_SYNC_EVENT_SYNC = 1,             /* primary pattern within 4 bit errors */
+    SDRGPU_SYNC_EVENT_INVERSION_90_CW = 2,  /* rotated pattern matched exactly: loop frequency corrected */
+    SDRGPU_SYNC_EVENT_INVERSION_90_CCW = 3,
+    SDRGPU_SYNC_EVENT_INVERSION_180 = 4,
+    SDRGPU_SYNC_EVENT_LOST = 5              /* MultiSyncPatternMatcher: more than the loss threshold of bits without a match */
+};
+sdrgpu_status sdrgpu_bank_set_sync_detector(sdrgpu_bank *b, int kind);
 /* loop state tap points of one channel: {pll phase, pll frequency, sampling point, detected samples/symbol} */
 sdrgpu_status sdrgpu_bank_get_loop_state(sdrgpu_bank *b, int channel, double *state4);
 /* 4 dibits per byte MSB first (J/dsp/symbol/DibitToByteBufferAssembler.java:58-93); host helper */

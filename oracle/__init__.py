@@ -94,6 +94,12 @@ def lib():
         "orc_psk_destroy": (None, [vp]),
         "orc_psk_receive": (C.c_int, [vp, _f32p, C.c_int, _u8p, _f32p]),
         "orc_psk_correct_inversion": (None, [vp, C.c_double]),
+        "orc_sync_create": (vp, [C.c_int, C.c_double]),
+        "orc_sync_destroy": (None, [vp]),
+        "orc_sync_delay": (C.c_int, [vp]),
+        "orc_sync_receive": (C.c_int, [vp, C.c_int, _f64p]),
+        "orc_psk_attach_sync": (None, [vp, vp]),
+        "orc_p25_chain_attach_sync": (C.c_int, [vp, C.c_int, C.c_double]),
         "orc_psk_reset_pll": (None, [vp]),
         "orc_psk_get_state": (None, [vp, _f64p, _f64p, _f32p, _f32p]),
         "orc_pack_dibits": (C.c_int, [_u8p, C.c_int, _u8p]),
@@ -437,6 +443,11 @@ class PSKDemodulator:
     def correct_inversion(self, correction):
         lib().orc_psk_correct_inversion(self._h, correction)
 
+    def attach_sync(self, sync):
+        """dibits become dibit | event << 2 and inversion corrections are applied (orc_psk_attach_sync)"""
+        self._sync = sync
+        lib().orc_psk_attach_sync(self._h, sync._h if sync is not None else None)
+
     def state(self):
         ph, fr, sp, ds = C.c_double(), C.c_double(), C.c_float(), C.c_float()
         lib().orc_psk_get_state(self._h, C.byref(ph), C.byref(fr), C.byref(sp), C.byref(ds))
@@ -445,6 +456,33 @@ class PSKDemodulator:
     def __del__(self):
         if getattr(self, "_h", None):
             lib().orc_psk_destroy(self._h)
+            self._h = None
+
+
+SYNC_P25_PHASE1, SYNC_P25_PHASE2 = 1, 2
+SYNC_EVENT_NONE, SYNC_EVENT_SYNC, SYNC_EVENT_90_CW, SYNC_EVENT_90_CCW, SYNC_EVENT_180, SYNC_EVENT_LOST = range(6)
+
+
+class SyncDetector:
+    """P25P1SyncDetector / P25P2SyncDetector behind the framer's dibit delay buffer, fed every dibit."""
+
+    def __init__(self, kind, sample_rate):
+        self._h = lib().orc_sync_create(kind, sample_rate)
+        if not self._h:
+            raise ValueError("unknown sync detector kind")
+
+    @property
+    def delay(self):
+        return lib().orc_sync_delay(self._h)
+
+    def receive(self, dibit):
+        corr = C.c_double()
+        ev = lib().orc_sync_receive(self._h, int(dibit), C.byref(corr))
+        return ev, corr.value
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orc_sync_destroy(self._h)
             self._h = None
 
 
@@ -468,6 +506,10 @@ class P25Chain:
         else:
             p, n = None, 0
         self._h = lib().orc_p25_chain_create(kind, sample_rate, p, n)
+
+    def attach_sync(self, sync_kind, sample_rate):
+        if lib().orc_p25_chain_attach_sync(self._h, sync_kind, sample_rate) != 0:
+            raise ValueError("unknown sync detector kind")
 
     def receive(self, iq, want_agc=False):
         a, p = _f32(iq)

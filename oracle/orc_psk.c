@@ -58,6 +58,7 @@ struct orc_psk {
     cpx prev_a, prev_b; /* DD: previousPreceding/previousCurrent; Gardner: previousMiddle/previousCurrent */
     cpx gardner_previous_symbol;
     cpx rot[4]; /* rotate-from +45, +135, -45, -135 */
+    orc_sync *sync; /* optional dibit listener (not owned) */
 };
 
 orc_psk *orc_psk_create(int kind, double sample_rate, double symbol_rate, double pll_bandwidth, float sample_counter_gain)
@@ -105,6 +106,8 @@ void orc_psk_correct_inversion(orc_psk *p, double correction)
     while (p->loop_frequency > p->max_loop_frequency) p->loop_frequency -= 2.0 * p->max_loop_frequency;
     while (p->loop_frequency < -p->max_loop_frequency) p->loop_frequency += 2.0 * p->max_loop_frequency;
 }
+
+void orc_psk_attach_sync(orc_psk *p, orc_sync *s) { p->sync = s; }
 
 /* CostasLoop.java:224-229 */
 void orc_psk_reset_pll(orc_psk *p)
@@ -279,6 +282,15 @@ int orc_psk_receive(orc_psk *p, const float *iq, int n_floats, uint8_t *dibits, 
         if (p->sampling_point < 1.0f) {
             float *t = taps ? taps + 4 * (size_t)n_symbols : NULL;
             int d = (p->kind == ORC_PSK_GARDNER) ? calculate_symbol_gardner(p, t) : calculate_symbol_dd(p, t);
+            /* calculateSymbol ends with broadcast(dibit): the framer's sync detector runs synchronously and may call
+             * correctInversion before the next sample is processed (P25P1SyncDetector.java:150-154) */
+            if (p->sync) {
+                double correction = 0.0;
+                int event = orc_sync_receive(p->sync, d, &correction);
+                if ((event & 7) >= ORC_SYNC_EVENT_INVERSION_90_CW && (event & 7) <= ORC_SYNC_EVENT_INVERSION_180)
+                    orc_psk_correct_inversion(p, correction);
+                d |= event << 2;
+            }
             dibits[n_symbols++] = (uint8_t)d;
         }
     }
@@ -310,6 +322,7 @@ struct orc_p25_chain {
     orc_cfir *fir;
     orc_psk *psk;
     float *tmp_a, *tmp_b;
+    orc_sync *sync;
 };
 
 orc_p25_chain *orc_p25_chain_create(int kind, double sample_rate, const float *fir_taps, int n_taps)
@@ -333,11 +346,20 @@ orc_p25_chain *orc_p25_chain_create(int kind, double sample_rate, const float *f
     return c;
 }
 
+int orc_p25_chain_attach_sync(orc_p25_chain *c, int sync_kind, double sample_rate)
+{
+    orc_sync_destroy(c->sync);
+    c->sync = orc_sync_create(sync_kind, sample_rate);
+    orc_psk_attach_sync(c->psk, c->sync);
+    return c->sync ? 0 : -1;
+}
+
 void orc_p25_chain_destroy(orc_p25_chain *c)
 {
     if (!c) return;
     orc_cfir_destroy(c->fir);
     orc_psk_destroy(c->psk);
+    orc_sync_destroy(c->sync);
     free(c->tmp_a);
     free(c->tmp_b);
     free(c);

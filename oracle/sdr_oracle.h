@@ -172,6 +172,26 @@ void orc_psk_get_state(const orc_psk *p, double *phase, double *freq, float *sam
 /* 4 dibits per byte, MSB first (DibitToByteBufferAssembler.java:58-93); returns whole bytes written */
 int orc_pack_dibits(const uint8_t *dibits, int n, uint8_t *out);
 
+/* ---------------------------------------------------------------- sync detection + PLL inversion feedback (8f #3) */
+enum { ORC_SYNC_P25_PHASE1 = 1, ORC_SYNC_P25_PHASE2 = 2 };
+/* event of one dibit: bits 0-2 one of these, bits 3-5 the primary detector's bit errors (SYNC only) */
+enum {
+    ORC_SYNC_EVENT_NONE = 0,
+    ORC_SYNC_EVENT_SYNC = 1,
+    ORC_SYNC_EVENT_INVERSION_90_CW = 2,
+    ORC_SYNC_EVENT_INVERSION_90_CCW = 3,
+    ORC_SYNC_EVENT_INVERSION_180 = 4,
+    ORC_SYNC_EVENT_LOST = 5
+};
+typedef struct orc_sync orc_sync;
+orc_sync *orc_sync_create(int kind, double sample_rate);
+void orc_sync_destroy(orc_sync *s);
+int orc_sync_delay(const orc_sync *s);
+int orc_sync_receive(orc_sync *s, int dibit, double *correction);
+/* the demodulator then feeds every dibit to s (as the framer's listener does, synchronously after the PLL update of
+ * that symbol), applies requested corrections with correctInversion and reports dibit | event << 2 per symbol */
+void orc_psk_attach_sync(orc_psk *p, orc_sync *s);
+
 /* ---------------------------------------------------------------- whole chains (a18) used as CPU baseline */
 typedef struct orc_p25_chain orc_p25_chain;
 /* kind: 0 = C4FM (FIR + AGC + DD, BW300, gain .3, 4800), 1 = LSM (no FIR, AGC, Gardner BW200 .3, 4800),
@@ -180,6 +200,8 @@ orc_p25_chain *orc_p25_chain_create(int kind, double sample_rate, const float *f
 void orc_p25_chain_destroy(orc_p25_chain *c);
 /* consumes whole 1024-complex-sample buffers only (the assembler framing); n_floats multiple of 2048 */
 int orc_p25_chain_receive(orc_p25_chain *c, const float *iq, int n_floats, uint8_t *dibits, float *agc_out);
+/* attaches a sync detector (owned by the chain) to the chain's demodulator */
+int orc_p25_chain_attach_sync(orc_p25_chain *c, int sync_kind, double sample_rate);
 
 #ifdef __cplusplus
 }

@@ -138,6 +138,11 @@ class Bank:
     def correctInversion(self, channel, radians):
         native.check(native.lib().sdrgpu_bank_correct_inversion(self._h, int(channel), float(radians)))
 
+    def setSyncDetector(self, kind):
+        """P25P1SyncDetector / P25P2SyncDetector + PLLPhaseInversionDetector feedback on the device
+        (native.SYNC_P25_PHASE1 / SYNC_P25_PHASE2 / SYNC_NONE).  Symbol bytes become dibit | event << 2 | errors << 5."""
+        native.check(native.lib().sdrgpu_bank_set_sync_detector(self._h, int(kind)))
+
     def resetPLL(self, channel):
         native.check(native.lib().sdrgpu_bank_reset_pll(self._h, int(channel)))
 

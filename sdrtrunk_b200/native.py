@@ -17,6 +17,9 @@ WINDOW_HAMMING, WINDOW_BLACKMAN = 0, 1
 DEMOD_NONE, DEMOD_FM, DEMOD_FM_SQUELCH, DEMOD_DQPSK_DECISION, DEMOD_DQPSK_GARDNER = 0, 1, 2, 3, 4
 FORMAT_F32, FORMAT_U8, FORMAT_S8, FORMAT_S16LE = 0, 1, 2, 3
 PRESET_P25_C4FM, PRESET_P25_LSM, PRESET_P25_HDQPSK, PRESET_NBFM, PRESET_DMR = 0, 1, 2, 3, 4
+SYNC_NONE, SYNC_P25_PHASE1, SYNC_P25_PHASE2 = 0, 1, 2
+(SYNC_EVENT_NONE, SYNC_EVENT_SYNC, SYNC_EVENT_INVERSION_90_CW, SYNC_EVENT_INVERSION_90_CCW, SYNC_EVENT_INVERSION_180,
+ SYNC_EVENT_LOST) = range(6)
 
 OK, ERR_INVALID_ARG, ERR_BAD_STATE, ERR_CUDA, ERR_OVERFLOW, ERR_DESIGN, ERR_NOMEM = range(7)
 
@@ -102,6 +105,7 @@ PROTOTYPES = {
     "sdrgpu_bank_process": (C.c_int, [_vp, _vp, C.c_longlong, C.c_int, C.c_int, _vp, C.c_int, _vp, C.c_longlong, _vp,
                                       C.c_int]),
     "sdrgpu_bank_correct_inversion": (C.c_int, [_vp, C.c_int, C.c_double]),
+    "sdrgpu_bank_set_sync_detector": (C.c_int, [_vp, C.c_int]),
     "sdrgpu_bank_reset_pll": (C.c_int, [_vp, C.c_int]),
     "sdrgpu_bank_get_loop_state": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_double)]),
     "sdrgpu_pack_dibits": (C.c_int, [_u8p, C.c_int, _u8p]),

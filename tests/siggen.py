@@ -124,3 +124,21 @@ def rel_rms(a, b):
     a = np.asarray(a, np.float64)
     b = np.asarray(b, np.float64)
     return float(np.sqrt(np.sum((a - b) ** 2) / max(np.sum(b ** 2), 1e-300)))
+
+
+# FrameSync.java:27-35 (dibits MSB first)
+P25_PHASE1_SYNC = 0x5575F5FF77FF
+P25_PHASE2_SYNC = 0x575D57F7FF
+
+
+def sync_dibits(pattern, n_bits):
+    return np.array([(pattern >> (n_bits - 2 - 2 * k)) & 3 for k in range(n_bits // 2)], np.uint8)
+
+
+def dibits_with_sync(rng, n_symbols, pattern, n_bits, first=40, period=180):
+    """random dibits with the sync pattern written every `period` symbols"""
+    d = rng.integers(0, 4, n_symbols).astype(np.uint8)
+    s = sync_dibits(pattern, n_bits)
+    for k in range(first, n_symbols - s.size, period):
+        d[k:k + s.size] = s
+    return d

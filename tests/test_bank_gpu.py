@@ -253,6 +253,86 @@ def test_psk_drop_in_classes(gpu):
     assert seen == want
 
 
+def _sync_case(kind, rng, n, offset, with_sync=True):
+    """a channel whose dibit stream carries the protocol's sync pattern every 180 symbols, at a carrier offset"""
+    p2 = kind == "hdqpsk"
+    rate = 6000.0 if p2 else 4800.0
+    n_sym = int(n * rate / 50000) + 8
+    pattern, bits = (sg.P25_PHASE2_SYNC, 40) if p2 else (sg.P25_PHASE1_SYNC, 48)
+    dib = sg.dibits_with_sync(rng, n_sym, pattern, bits) if with_sync else rng.integers(0, 4, n_sym).astype(np.uint8)
+    tp = rng.uniform(0, 1)
+    if kind == "c4fm":
+        z = sg.c4fm(dib, carrier_offset=offset, timing_phase=tp, n_samples=n, amplitude=0.5)
+    else:
+        z = sg.dqpsk(dib, symbol_rate=rate, carrier_offset=offset, timing_phase=tp, n_samples=n, amplitude=0.5)
+    return sg.interleave(z + sg.awgn(rng, n, 0.01))
+
+
+@pytest.mark.parametrize("kind", ["c4fm", "lsm", "hdqpsk"])
+def test_sync_detector_and_inversion_feedback_on_device(gpu, kind):
+    """the framer's sync detector + PLLPhaseInversionDetector feedback run inside the demodulator
+    kernel.  Channels locked 90 / 180 degrees off (carrier offset = +-rate/4, rate/2) must be corrected at the very
+    symbol the reference corrects them: every byte (dibit | event << 2 | errors << 5) equals the oracle's."""
+    from sdrtrunk_b200.dsp import Bank
+    preset, okind, taps = _preset(gpu, kind)
+    skind, okind_sync, rate = ((gpu.SYNC_P25_PHASE2, oracle.SYNC_P25_PHASE2, 6000.0) if kind == "hdqpsk"
+                               else (gpu.SYNC_P25_PHASE1, oracle.SYNC_P25_PHASE1, 4800.0))
+    rng = np.random.default_rng({"c4fm": 31, "lsm": 32, "hdqpsk": 33}[kind])
+    n = 24 * 1024
+    offsets = [0.0, rate / 4 - 50, -rate / 4 - 50, rate / 2 - 100, 120.0, -rate / 4 + 30, rate / 4, 0.0]
+    x = np.stack([_sync_case(kind, rng, n, off, with_sync=(k != 7)) for k, off in enumerate(offsets)])
+    bank = Bank.preset(preset, len(offsets), 50000.0, taps, max_samples_per_call=8 * 1024)
+    bank.setSyncDetector(skind)
+    parts = [bank.process(x[:, 2 * a:2 * b]) for a, b in ((0, 8192), (8192, 9000), (9000, 17000), (17000, n))]
+    seen = set()
+    for k in range(len(offsets)):
+        got = np.concatenate([p[k] for p in parts])
+        chain = oracle.P25Chain(okind, 50000.0, taps)
+        chain.attach_sync(okind_sync, 50000.0)
+        want = chain.receive(x[k])
+        assert got.size == want.size, k
+        assert np.array_equal(got, want), (k, np.nonzero(got != want)[0][:5])
+        events = (want >> 2) & 7
+        seen |= set(int(e) for e in events[events > 0])
+        if k in (1, 2, 3):      # rotated pattern first, normal ones after the correction
+            first = events[events > 0]
+            assert first[0] in (gpu.SYNC_EVENT_INVERSION_90_CW, gpu.SYNC_EVENT_INVERSION_90_CCW, gpu.SYNC_EVENT_INVERSION_180), k
+            assert np.all(first[1:] == gpu.SYNC_EVENT_SYNC) and first.size >= 8, k
+    assert {gpu.SYNC_EVENT_SYNC, gpu.SYNC_EVENT_INVERSION_90_CW, gpu.SYNC_EVENT_INVERSION_90_CCW,
+            gpu.SYNC_EVENT_INVERSION_180, gpu.SYNC_EVENT_LOST} <= seen
+    # switching the detector off restores plain dibits; switching it on again starts from a fresh detector
+    bank2 = Bank.preset(preset, 1, 50000.0, taps, max_samples_per_call=n)
+    bank2.setSyncDetector(skind)
+    bank2.setSyncDetector(gpu.SYNC_NONE)
+    assert np.array_equal(bank2.process(x[:1])[0], oracle.P25Chain(okind, 50000.0, taps).receive(x[0]))
+    with pytest.raises(gpu.IllegalArgumentException):
+        bank2.setSyncDetector(7)
+
+
+def test_sync_detector_thread_per_channel_kernel(gpu):
+    """the same through psk_wide_kernel (>= 3000 channels): six distinct channels tiled over 3072"""
+    from sdrtrunk_b200.dsp import Bank
+    taps = c4fm_taps()
+    rng = np.random.default_rng(34)
+    n = 10 * 1024
+    offsets = [0.0, 1150.0, -1250.0, 2300.0, 90.0, -60.0]
+    base = np.stack([_sync_case("c4fm", rng, n, off) for off in offsets])
+    c = 3072
+    x = np.tile(base, (c // len(offsets), 1))
+    bank = Bank.preset(gpu.PRESET_P25_C4FM, c, 50000.0, taps, max_samples_per_call=n)
+    bank.setSyncDetector(gpu.SYNC_P25_PHASE1)
+    got = bank.process(x[:, :2 * 6 * 1024])
+    got2 = bank.process(x[:, 2 * 6 * 1024:])
+    want = []
+    for k in range(len(offsets)):
+        chain = oracle.P25Chain(oracle.C4FM, 50000.0, taps)
+        chain.attach_sync(oracle.SYNC_P25_PHASE1, 50000.0)
+        want.append(chain.receive(base[k]))
+    assert any(np.any(((w >> 2) & 7) >= 2) for w in want)
+    for k in range(c):
+        assert np.array_equal(np.concatenate([got[k], got2[k]]), want[k % len(offsets)]), k
+
+
 @pytest.mark.parametrize("c", [1024, 3072])
 def test_many_channels(gpu, c):
     """BASELINE config 4 shape: >= 1000 channel-domain streams; every channel gets the same input so that one

@@ -190,3 +190,106 @@ def test_oscillator_mix_shifts_frequency():
     step = np.angle(np.mean(out[1:] * np.conj(out[:-1])))
     assert abs(step - 2 * np.pi * 1000 / 50000.0) < 1e-4
     assert abs(np.abs(out[-1]) - 1.0) < 1e-3
+
+
+# ------------------------------------------------------------------------------------------------ sync detection
+class _JavaMatcher:
+    """MultiSyncPatternMatcher + detectors restated independently of orc_sync.c with Python integers
+    (explicit 64-bit rotateLeft, per-bit feeding), behind a DibitDelayBuffer."""
+
+    def __init__(self, patterns, sync_size, loss_threshold, delay):
+        self.patterns, self.mask, self.loss = patterns, (1 << sync_size) - 1, loss_threshold
+        self.bits, self.count = 0, 0
+        self.buffer, self.pointer = [0] * delay, 0
+
+    @staticmethod
+    def _rotl(v):
+        return ((v << 1) | (v >> 63)) & 0xFFFFFFFFFFFFFFFF
+
+    def receive(self, dibit):
+        delayed = self.buffer[self.pointer]
+        self.buffer[self.pointer] = dibit
+        self.pointer = (self.pointer + 1) % len(self.buffer)
+        for bit in (delayed >> 1, delayed & 1):
+            self.bits = self._rotl(self.bits) & self.mask
+            if bit:
+                self.bits += 1
+        self.count += 2
+        event = 0
+        errors = bin(self.bits ^ self.patterns[0]).count("1")
+        if errors <= 4:
+            event, self.count = 1 | (errors << 3), 0
+        for k in (1, 2, 3):
+            if self.bits == self.patterns[k]:
+                event, self.count = 1 + k, 0
+        if self.count > self.loss:
+            event, self.count = 5, 0
+        return event
+
+
+@pytest.mark.parametrize("kind", ["phase1", "phase2"])
+def test_sync_detector_events(kind):
+    if kind == "phase1":
+        okind, pats, bits, loss, delay, rate = oracle.SYNC_P25_PHASE1, (0x5575F5FF77FF, 0x001050551155, 0xFFEFAFAAEEAA, 0xAA8A0A008800), 48, 1568, 33, 4800.0
+    else:
+        okind, pats, bits, loss, delay, rate = oracle.SYNC_P25_PHASE2, (0x575D57F7FF, 0x0104015155, 0xFEFBFEAEAA, 0xA8A2A80800), 40, 1440, 160, 6000.0
+    rng = np.random.default_rng(bits)
+    d = rng.integers(0, 4, 6000).astype(np.uint8)
+    d[2000:3700] = rng.integers(0, 4, 1700)           # a long stretch without any pattern -> sync loss events
+    want_at = {}
+    pos = 100
+    for k, flips in ((0, 0), (0, 3), (0, 4), (0, 5), (1, 0), (2, 0), (3, 0), (1, 1), (0, 2)):
+        v = pats[k]
+        for b in rng.choice(bits, flips, replace=False):
+            v ^= 1 << int(b)
+        d[pos:pos + bits // 2] = sg.sync_dibits(v, bits)
+        # raised when the last dibit of the pattern leaves the delay buffer
+        expect = (1 | (flips << 3)) if (k == 0 and flips <= 4) else ((1 + k) if (k > 0 and flips == 0) else 0)
+        want_at[pos + bits // 2 - 1 + delay] = expect
+        pos += 190
+    det, ref = oracle.SyncDetector(okind, 50000.0), _JavaMatcher(pats, bits, loss, delay)
+    assert det.delay == delay
+    events, corrections = [], []
+    for x in d:
+        ev, corr = det.receive(x)
+        events.append(ev)
+        corrections.append(corr)
+        assert ev == ref.receive(int(x))
+    for at, ev in want_at.items():
+        assert events[at] == ev, (at, ev, events[at])
+    assert events.count(5) >= 1 and all(events[k] == 0 for k in range(delay))
+    # PLLPhaseInversionDetector.mPllCorrection = 2 pi (+-rate/4 | rate/2) / fs, only with the exact rotated patterns
+    by_event = {2: rate / 4, 3: -rate / 4, 4: rate / 2}
+    for ev, corr in zip(events, corrections):
+        assert corr == (2.0 * np.pi * by_event[ev] / 50000.0 if ev in by_event else 0.0)
+
+
+@pytest.mark.parametrize("offset,event", [(0.0, None), (1150.0, oracle.SYNC_EVENT_90_CCW), (-1250.0, oracle.SYNC_EVENT_90_CW),
+                                          (2300.0, oracle.SYNC_EVENT_180)])
+def test_inversion_feedback_recovers_a_falsely_locked_loop(offset, event):
+    """A carrier offset of a quarter / half of the symbol rate locks the Costas loop 90 / 180 degrees per symbol off:
+    dibits come out rotated until the rotated sync pattern is seen and correctInversion is applied; from then on the
+    normal pattern is found and the payload decodes (P25P1SyncDetector.java:122-130)."""
+    import scipy.signal as ss
+    taps = ss.remez(72, [0, 5100, 6500, 25000], [1, 0], fs=50000).astype(np.float32)
+    rng = np.random.default_rng(11)
+    d = sg.dibits_with_sync(rng, 2000, sg.P25_PHASE1_SYNC, 48)
+    n = 20 * 1024
+    x = sg.interleave(sg.c4fm(d, carrier_offset=offset, n_samples=n, amplitude=0.5) + sg.awgn(rng, n, 0.01))
+    plain = oracle.P25Chain(oracle.C4FM, 50000.0, taps).receive(x)
+    chain = oracle.P25Chain(oracle.C4FM, 50000.0, taps)
+    chain.attach_sync(oracle.SYNC_P25_PHASE1, 50000.0)
+    out = chain.receive(x)
+    ev = (out >> 2) & 7
+    hits = [(int(i), int(ev[i])) for i in np.nonzero(ev)[0]]
+    if event is None:
+        assert np.array_equal(out & 3, plain) and all(e == oracle.SYNC_EVENT_SYNC for _, e in hits) and len(hits) >= 9
+    else:
+        assert hits[0][1] == event and all(e == oracle.SYNC_EVENT_SYNC for _, e in hits[1:]) and len(hits) >= 9
+        first = hits[0][0]
+        assert np.array_equal((out & 3)[:first + 1], plain[:first + 1])       # identical until the correction
+        lag = 5                                                               # filter + interpolator delay in symbols
+        got, truth = (out & 3)[first + 40 + lag:], d[first + 40:]
+        m = min(got.size, truth.size) - 8
+        assert np.mean(got[:m] == truth[:m]) > 0.99                           # decodes the payload afterwards
+        assert np.mean(plain[first + 40 + lag:][:m] == truth[:m]) < 0.5       # which the uncorrected loop never does

@@ -79,3 +79,42 @@ def test_half_band_stage_plan_is_the_references():
         wins = re.findall(r"WINDOW_TYPE = Window\.WindowType\.(\w+)", src)
         assert [int(v) for v in found] == [stages[0][0]], (rate, found)
         assert wins == [stages[0][1]], (rate, wins)
+
+
+def test_sync_patterns_and_detector_constants():
+    """FrameSync patterns, match threshold, delay lengths and PLL corrections of the P25 sync detectors, as carried by
+    the oracle (orc_sync.c) and the product (SyncTraits in bank.cu)."""
+    fs = dict((k, int(v, 16)) for k, v in re.findall(r"(P25_PHASE\d_\w+)\(\s*0x([0-9A-Fa-f]+)l\s*\)", java("dsp/symbol/FrameSync.java")))
+    assert len(fs) == 8
+    for src in (open(os.path.join(ROOT, "oracle", "orc_sync.c")).read(),
+                open(os.path.join(ROOT, "sdrtrunk_b200", "csrc", "bank.cu")).read()):
+        mine = set(int(v, 16) for v in re.findall(r"0x([0-9A-Fa-f]{10,12})ull", src))
+        assert set(fs.values()) <= mine
+    p1 = java("module/decode/p25/phase1/P25P1SyncDetector.java")
+    p2 = java("module/decode/p25/phase2/P25P2SyncDetector.java")
+    assert "SYNC_MATCH_THRESHOLD = 4" in p1 and "SYNC_MATCH_THRESHOLD = 4" in p2
+    assert "DEFAULT_SYMBOL_RATE = 4800" in p1 and "DEFAULT_SYMBOL_RATE = 6000" in p2
+    assert "getMessageLength(), 48)" in p1 and "MultiSyncPatternMatcher(syncDetectListener, 1440, 40)" in p2
+    assert "LOGICAL_LINK_DATA_UNIT_1(5, 1568," in java("module/decode/p25/phase1/P25P1DataUnitID.java")
+    dud = java("module/decode/p25/phase1/P25P1DataUnitDetector.java")
+    assert "DATA_UNIT_DIBIT_LENGTH = 57" in dud and "SYNC_DIBIT_LENGTH = 24" in dud
+    assert "new DibitDelayBuffer(160)" in java("module/decode/p25/phase2/P25P2SuperFrameDetector.java")
+    assert oracle.SyncDetector(oracle.SYNC_P25_PHASE1, 50000.0).delay == 57 - 24
+    assert oracle.SyncDetector(oracle.SYNC_P25_PHASE2, 50000.0).delay == 160
+    # the rotated patterns are the normal one with every dibit's constellation point turned by 90 / 180 degrees:
+    # +1 (00) -> +3 (01) -> -3 (11) -> -1 (10) -> +1 going counter-clockwise
+    ccw = {0: 1, 1: 3, 3: 2, 2: 0}
+    for phase, bits in (("PHASE1", 48), ("PHASE2", 40)):
+        d = [(fs["P25_%s_NORMAL" % phase] >> (bits - 2 - 2 * k)) & 3 for k in range(bits // 2)]
+        def rotate(seq, quarter_turns):
+            for _ in range(quarter_turns):
+                seq = [ccw[v] for v in seq]
+            return seq
+        def pack(seq):
+            v = 0
+            for x in seq:
+                v = (v << 2) | x
+            return v
+        assert pack(rotate(d, 1)) == fs["P25_%s_ERROR_90_CCW" % phase]
+        assert pack(rotate(d, 2)) == fs["P25_%s_ERROR_180" % phase]
+        assert pack(rotate(d, 3)) == fs["P25_%s_ERROR_90_CW" % phase]
