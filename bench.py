@@ -487,11 +487,11 @@ class GpuWorkload:
     def step_device(self):
         n, L = self.native, self.L
         if self.pipeline is None:
-            n.check(L.sdrgpu_chan_process(self.chan._h, C.c_void_p(self.x_dev.data_ptr()), self.n_floats, n.DEVICE,
+            n.check(L.sdrgpu_chan_process(self.chan._h, C.c_void_p(getattr(self, '_dev_in', self.x_dev).data_ptr()), self.n_floats, n.DEVICE,
                                           C.c_void_p(self.out_dev.data_ptr()), 2 * self.n_blocks, n.DEVICE,
                                           n.LAYOUT_CHANNELS, None))
         else:
-            n.check(L.sdrgpu_pipeline_process(self.pipeline._h, C.c_void_p(self.x_dev.data_ptr()), self.n_floats,
+            n.check(L.sdrgpu_pipeline_process(self.pipeline._h, C.c_void_p(getattr(self, '_dev_in', self.x_dev).data_ptr()), self.n_floats,
                                               n.DEVICE, C.c_void_p(self.sym_dev.data_ptr()), self.sym_stride, None, 0,
                                               C.c_void_p(self.cnt_dev.data_ptr()), n.DEVICE))
 
@@ -516,6 +516,22 @@ class GpuWorkload:
             del q
         self.chan.setSampleFormat("u8" if on else "f32")
         self._host_in = self.x_host_u8 if on else self.x_host
+
+    def enable_airspy_input(self, on):
+        """section 8f #1: Airspy native buffers (packed 12-bit real samples at twice the complex rate, 3 bytes per
+        complex sample), unpacked + DC-removed + Hilbert-transformed on the device (AirspySampleConverter).  Random ADC
+        codes: this leg measures throughput, parity is tests/."""
+        torch = self.torch
+        if on and not hasattr(self, "x_host_airspy"):
+            g = torch.Generator(device=self.dev)
+            g.manual_seed(77)
+            nbytes = self.n_floats // 2 * 3
+            self.x_dev_airspy = torch.randint(0, 256, (nbytes,), dtype=torch.uint8, device=self.dev, generator=g)
+            self.x_host_airspy = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+            self.x_host_airspy.copy_(self.x_dev_airspy)
+        self.chan.setSampleFormat("airspy_packed" if on else "f32")
+        self._host_in = self.x_host_airspy if on else self.x_host
+        self._dev_in = self.x_dev_airspy if on else self.x_dev
 
     def sanity(self):
         """decoded-vs-transmitted dibits of a few channels (first pass from reset state would be needed for an exact
@@ -593,6 +609,20 @@ def measure(w, args, world, dist, barrier):
         e2e_u8 = {"value": w.n_complex * world / (u8_ms * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": w.n_floats,
                   "d2h_bytes_per_step": w.d2h, "ms_per_step": u8_ms,
                   "input": "unsigned 8-bit tuner samples (ByteSampleConverter format), converted on the device"}
+    airspy = None
+    if w.pipeline is None:   # channelizer only: random ADC codes would drive the demodulators of the chain off their locks
+        w.enable_airspy_input(True)
+        ms_a_dev, _ = timed(w.step_device, args.steps, 3)
+        airspy = {"input": "Airspy packed 12-bit real samples (3 bytes per complex sample): unpack + DC removal + Hilbert "
+                           "transform on the device in front of the channelizer",
+                  "device_resident": {"ms_per_step": ms_a_dev / args.steps,
+                                      "value": w.n_complex * world / (ms_a_dev / args.steps * 1e-3) / 1e6, "unit": UNIT}}
+        if not args.device_only:
+            ms_a_host, wall_a = timed(w.step_host, args.steps, 3)
+            a_ms = max(ms_a_host, wall_a) / args.steps
+            airspy["e2e"] = {"value": w.n_complex * world / (a_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": a_ms,
+                             "h2d_bytes_per_step": w.n_floats // 2 * 3, "d2h_bytes_per_step": w.d2h}
+        w.enable_airspy_input(False)
     kernels = w.kernel_times(min(args.steps, 10))
     with_sync = None
     if w.pipeline is not None:
@@ -608,7 +638,7 @@ def measure(w, args, world, dist, barrier):
     e2e_ms = max(ms_e2e_dev, wall_e2e) / args.steps
     return {"ms_per_step": ms_per_step, "value": total / (ms_per_step * 1e-3) / 1e6,
             "e2e_ms": e2e_ms, "e2e_value": total / (e2e_ms * 1e-3) / 1e6, "launches": launches, "kernels": kernels,
-            "sanity": sanity, "e2e_u8": e2e_u8, "with_sync": with_sync}
+            "sanity": sanity, "e2e_u8": e2e_u8, "with_sync": with_sync, "airspy": airspy}
 
 
 def run_gpu(args, rank, world, local_rank):
@@ -674,6 +704,7 @@ def run_gpu(args, rank, world, local_rank):
                          "d2h_bytes_per_step": w2.d2h, "ms_per_step": r2["e2e_ms"]},
                  "e2e_u8_input": r2["e2e_u8"],
                  "with_sync_detector": r2["with_sync"],
+                 "airspy_input": r2["airspy"],
                  "gpu_launches": r2["launches"], "kernels_ms": r2["kernels"], "roofline": roofline_of(w2, r2),
                  "decode_sanity": r2["sanity"]}
         del w2
@@ -710,6 +741,8 @@ def run_gpu(args, rank, world, local_rank):
         line["decode_sanity"] = r["sanity"]
     if r.get("with_sync") is not None:
         line["with_sync_detector"] = r["with_sync"]
+    if r.get("airspy") is not None:
+        line["airspy_input"] = r["airspy"]
     if extra is not None:
         line["chain_c4fm"] = extra
     print(json.dumps(line))

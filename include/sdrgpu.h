@@ -82,9 +82,34 @@ sdrgpu_status sdrgpu_center_frequency_for_indexes(double sample_rate, int channe
  * (SignedByteSampleConverter.java:21-35: x / 128.0f), little-endian signed 16-bit
  * (J/sample/ConversionUtils.java:22-34: x / 32767.0f).  Converting on the device cuts the host-to-device copy to
  * 1-2 bytes per value instead of 4. */
-enum { SDRGPU_FORMAT_F32 = 0, SDRGPU_FORMAT_U8 = 1, SDRGPU_FORMAT_S8 = 2, SDRGPU_FORMAT_S16LE = 3 };
-/* n_values sample values (I and Q count separately) from src (format) to float dst */
+enum {
+    SDRGPU_FORMAT_F32 = 0,
+    SDRGPU_FORMAT_U8 = 1,
+    SDRGPU_FORMAT_S8 = 2,
+    SDRGPU_FORMAT_S16LE = 3,
+    /* Airspy native buffers: 12-bit REAL samples at twice the complex rate, two bytes per sample little-endian or
+     * "sample packing" (two samples in three bytes).  Stateful (DC removal + Hilbert transform, see sdrgpu_airspy
+     * below): accepted by sdrgpu_chan_set_input_format only; n_floats of a process call then counts real samples,
+     * which is also the number of floats of the I/Q stream they become. */
+    SDRGPU_FORMAT_AIRSPY_U16LE = 4,
+    SDRGPU_FORMAT_AIRSPY_PACKED12 = 5
+};
+/* n_values sample values (I and Q count separately) from src (format U8 / S8 / S16LE) to float dst */
 sdrgpu_status sdrgpu_convert_samples(int format, const void *src, int src_mem, int n_values, float *dst, int dst_mem);
+
+/* AirspySampleConverter (J/source/tuner/airspy/AirspySampleConverter.java:27-158): unpack -> DCRemovalFilter(0.01f)
+ * (J/dsp/filter/dc/DCRemovalFilter.java:52-67) -> HilbertTransform.filter (J/dsp/filter/hilbert/HilbertTransform.java:
+ * 88-132, coefficients from Filters.HALF_BAND_FILTER_47T).  Bit-exact with the Java: the sequential DC recursion is
+ * run speculatively in 4 096-sample segments and verified (airspy.cu).  State (DC average, the Hilbert filter's last 47
+ * samples, the fs/2 sign) carries over from call to call as in the Java object. */
+typedef struct sdrgpu_airspy sdrgpu_airspy;
+sdrgpu_status sdrgpu_airspy_create(sdrgpu_airspy **a, int max_samples);   /* real samples per call, even */
+sdrgpu_status sdrgpu_airspy_destroy(sdrgpu_airspy *a);
+sdrgpu_status sdrgpu_airspy_set_sample_packing(sdrgpu_airspy *a, int enabled);   /* AirspySampleConverter.setSamplePacking */
+/* n_samples (even) raw samples -> n_samples floats of interleaved I/Q (n_samples / 2 complex samples) */
+sdrgpu_status sdrgpu_airspy_convert(sdrgpu_airspy *a, const void *raw, int raw_mem, int n_samples, float *iq, int iq_mem);
+/* diagnostics: segments whose speculative start had to be redone sequentially since creation (expected 0) */
+sdrgpu_status sdrgpu_airspy_mismatches(sdrgpu_airspy *a, int *count);
 
 /* ------------------------------------------------------------------ polyphase channelizer
  * Replaces ComplexPolyphaseChannelizerM2.receive + process + IFFTProcessor

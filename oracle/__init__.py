@@ -94,6 +94,9 @@ def lib():
         "orc_psk_destroy": (None, [vp]),
         "orc_psk_receive": (C.c_int, [vp, _f32p, C.c_int, _u8p, _f32p]),
         "orc_psk_correct_inversion": (None, [vp, C.c_double]),
+        "orc_airspy_create": (vp, []),
+        "orc_airspy_destroy": (None, [vp]),
+        "orc_airspy_convert": (C.c_int, [vp, _u8p, C.c_int, C.c_int, _f32p]),
         "orc_sync_create": (vp, [C.c_int, C.c_double]),
         "orc_sync_destroy": (None, [vp]),
         "orc_sync_delay": (C.c_int, [vp]),
@@ -456,6 +459,29 @@ class PSKDemodulator:
     def __del__(self):
         if getattr(self, "_h", None):
             lib().orc_psk_destroy(self._h)
+            self._h = None
+
+
+class AirspySampleConverter:
+    """AirspySampleConverter: raw 12-bit real samples -> DC removal -> Hilbert transform -> interleaved I/Q."""
+
+    def __init__(self):
+        self._h = lib().orc_airspy_create()
+        self.packed = False
+
+    def setSamplePacking(self, enabled):
+        self.packed = bool(enabled)
+
+    def convert(self, raw):
+        b = np.ascontiguousarray(raw, np.uint8)
+        n = b.size // 3 * 2 if self.packed else b.size // 2
+        out = np.zeros(max(n, 1), np.float32)
+        got = lib().orc_airspy_convert(self._h, b.ctypes.data_as(_u8p), b.size, 1 if self.packed else 0, out.ctypes.data_as(_f32p))
+        return out[:got]
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orc_airspy_destroy(self._h)
             self._h = None
 
 

@@ -102,6 +102,14 @@ void orc_convert_u8(const uint8_t *in, int n, float *out);
 void orc_convert_s8(const int8_t *in, int n, float *out);
 void orc_convert_s16le(const uint8_t *in, int n, float *out);
 
+/* Airspy native buffers (12-bit real samples at twice the complex rate): unpack -> DCRemovalFilter(0.01f) ->
+ * HilbertTransform.  n_bytes: 2 per sample (unpacked) or 3 per 2 samples (packed); returns the number of floats written
+ * to out (one per real sample = interleaved I/Q of half as many complex samples).  State carries over between calls. */
+typedef struct orc_airspy orc_airspy;
+orc_airspy *orc_airspy_create(void);
+void orc_airspy_destroy(orc_airspy *a);
+int orc_airspy_convert(orc_airspy *a, const uint8_t *bytes, int n_bytes, int packed, float *out);
+
 /* ---------------------------------------------------------------- decimation (a9, a10) */
 typedef struct orc_halfband orc_halfband;
 orc_halfband *orc_halfband_create(const float *coefficients, int length);

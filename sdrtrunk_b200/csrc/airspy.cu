@@ -1,0 +1,420 @@
+// Airspy native-buffer conversion on the device: AirspySampleConverter.convert
+// (J/source/tuner/airspy/AirspySampleConverter.java:70-158) = unpack 12-bit real samples -> DCRemovalFilter(0.01f)
+// (J/dsp/filter/dc/DCRemovalFilter.java:52-67) -> HilbertTransform.filter (J/dsp/filter/hilbert/HilbertTransform.java:
+// 88-132).  The tuner delivers real samples at twice the complex rate; two of them make one complex sample, so the
+// sample-value count of a buffer equals the float count of the I/Q stream it becomes.
+//
+// DC removal is a float recursion over the whole stream (average += 0.01f * (x - average)): sequential by
+// definition, 12 cycles per sample on one thread = 160 MS/s.  It is contractive, though, and in float arithmetic two
+// runs started from different averages become bit-identical after ~1 600 samples (and stay so).  So the stream is
+// cut into 2 048-sample segments, one thread each; a thread starts 4 096 samples early from a guessed average of 0,
+// and a second kernel checks that the value every segment arrived at on its first sample equals the value its
+// predecessor ended on.  If all checks hold -- they do unless the input is pathological -- the outputs are exactly
+// the sequential ones by induction from segment 0, which starts from the true carried state.  Otherwise a single
+// thread redoes the call's samples from the carried state (correct, slow, never seen in practice).
+//
+// The Hilbert transform is a plain FIR once the Java's circular buffer + index map are unrolled (checked against
+// the literal restatement in oracle/orc_airspy.c): with n the second sample of pair k,
+//     I[k] = s * f[n - 24],   Q[k] = s * sum_{x = 0, 2, .., 22} h[x] * (f[n - 47 + x] - f[n - x - 1]),   s = (-1)^k
+// accumulated in x order with separately rounded products (no FMA), h[x] = 2 * -|halfband47[x]|.
+#include <cmath>
+#include <cstdint>
+
+#include "common.cuh"
+
+using namespace sdrgpu;
+
+namespace {
+
+constexpr int kSegment = 2048;   // samples per thread of the DC stage (more, shorter segments: more warps to hide latency)
+constexpr int kWarmup = 4096;    // samples a thread runs ahead of its segment from the guessed state
+constexpr int kHistory = 47;     // HilbertTransform: the filter length; ages 1 .. 47 behind the newest sample
+constexpr float kRatio = 0.01f;  // AirspySampleConverter.java:31
+
+// Filters.HALF_BAND_FILTER_47T (J/dsp/filter/Filters.java:1708-1722), even taps left of the centre, turned into
+// Hilbert coefficients by HilbertTransform.convertHalfBandToHilbert (:223-244): 2.0f * -|c|
+__constant__ float c_hilbert[12];
+const float kHalfBandLeft[12] = {-0.000998606272947510f, 0.001695637278417295f, -0.003054430179754289f, 0.005055504379767936f,
+                                 -0.007901319195893647f, 0.011873357051047719f, -0.017411159379930066f, 0.025304817427568772f,
+                                 -0.037225225204559217f, 0.057533286997004301f, -0.102327462004259350f, 0.317034472508947400f};
+
+struct AirspyState {
+    float average;   // DCRemovalFilter.mAverage
+    int inverted;    // HilbertTransform.mInvertFlag
+    int mismatches;  // segments whose guessed start turned out wrong in the last call
+    int pad;
+};
+
+// AirspySampleConverter.scale of sample i of the raw buffer (convertUnpacked :92-110 / convertPacked :118-149)
+__device__ __forceinline__ float raw_sample(const uint8_t *__restrict__ raw, size_t i, bool packed)
+{
+    int v;
+    if (!packed) {
+        v = (int)raw[2 * i] | ((int)raw[2 * i + 1] << 8);
+    } else {
+        const uint8_t *p = raw + 3 * (i >> 1);
+        v = (i & 1) ? ((((int)p[1] << 8) & 0xF00) | (int)p[2]) : ((((int)p[0] << 4) & 0xFF0) | (((int)p[1] >> 4) & 0xF));
+    }
+    return __fmul_rn((float)((v & 0xFFF) - 2048), 1.0f / 2048.0f);
+}
+
+// 32 samples starting at sample i (a multiple of 32) are 64 (unpacked) or 48 (packed) bytes: four / three 16-byte loads.
+// Loading and unpacking are separate so that the next group's loads are in flight while this group runs the recursion.
+struct RawGroup {
+    uint4 w[4];
+};
+
+__device__ __forceinline__ RawGroup load_group(const uint8_t *__restrict__ raw, size_t i, bool packed)
+{
+    RawGroup g;
+    if (!packed) {
+        const uint4 *p = reinterpret_cast<const uint4 *>(raw + 2 * i);
+#pragma unroll
+        for (int q = 0; q < 4; q++) g.w[q] = __ldg(p + q);
+    } else {
+        const uint4 *p = reinterpret_cast<const uint4 *>(raw + 3 * (i >> 1));
+#pragma unroll
+        for (int q = 0; q < 3; q++) g.w[q] = __ldg(p + q);
+        g.w[3] = make_uint4(0, 0, 0, 0);
+    }
+    return g;
+}
+
+__device__ __forceinline__ void unpack_group(const RawGroup &g, bool packed, float *x)
+{
+    unsigned u[16];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        u[4 * q] = g.w[q].x;
+        u[4 * q + 1] = g.w[q].y;
+        u[4 * q + 2] = g.w[q].z;
+        u[4 * q + 3] = g.w[q].w;
+    }
+    if (!packed) {
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            x[2 * j] = __fmul_rn((float)((int)(u[j] & 0xFFF) - 2048), 1.0f / 2048.0f);
+            x[2 * j + 1] = __fmul_rn((float)((int)((u[j] >> 16) & 0xFFF) - 2048), 1.0f / 2048.0f);
+        }
+    } else {
+        // three little-endian words hold eight samples: bytes b0 .. b11, pair j = bytes 3j .. 3j+2
+#pragma unroll
+        for (int g3 = 0; g3 < 4; g3++) {
+            const unsigned w0 = u[3 * g3], w1 = u[3 * g3 + 1], w2 = u[3 * g3 + 2];
+            const unsigned b[12] = {w0 & 255, (w0 >> 8) & 255, (w0 >> 16) & 255, w0 >> 24, w1 & 255, (w1 >> 8) & 255,
+                                    (w1 >> 16) & 255, w1 >> 24, w2 & 255, (w2 >> 8) & 255, (w2 >> 16) & 255, w2 >> 24};
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int first = (int)((b[3 * j] << 4) | (b[3 * j + 1] >> 4));
+                const int second = (int)(((b[3 * j + 1] & 0xF) << 8) | b[3 * j + 2]);
+                x[8 * g3 + 2 * j] = __fmul_rn((float)(first - 2048), 1.0f / 2048.0f);
+                x[8 * g3 + 2 * j + 1] = __fmul_rn((float)(second - 2048), 1.0f / 2048.0f);
+            }
+        }
+    }
+}
+
+// DCRemovalFilter.filter(float): filtered = sample - average; average += ratio * filtered
+__device__ __forceinline__ float dc_step(float &average, float x)
+{
+    const float filtered = __fsub_rn(x, average);
+    average = __fadd_rn(average, __fmul_rn(kRatio, filtered));
+    return filtered;
+}
+
+// One thread per segment.  filtered: this call's samples (the caller placed kHistory older ones in front of it).
+__global__ void __launch_bounds__(32) airspy_dc_kernel(const uint8_t *__restrict__ raw, int n, int packed, int aligned,
+                                                         const AirspyState *__restrict__ state, float *__restrict__ filtered,
+                                                         float *__restrict__ seg_start, float *__restrict__ seg_end)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const long long begin = (long long)k * kSegment;
+    if (begin >= n) return;
+    const int end = (int)min((long long)n, begin + kSegment);
+    const int from = begin > kWarmup ? (int)begin - kWarmup : 0;
+    float average = from == 0 ? state->average : 0.0f;
+    const bool pk = packed != 0;
+    // kSegment and kWarmup are multiples of 32, so whole groups of 32 samples cover everything but the call's tail
+    int i = from;
+    if (aligned && i + 32 <= end) {
+        // groups [from, groups_end) in steps of 32; those before `begin` only warm the average up
+        const int groups_end = from + (end - from) / 32 * 32;
+        RawGroup next = load_group(raw, (size_t)i, pk);
+        for (; i < groups_end; i += 32) {
+            const RawGroup cur = next;
+            if (i + 32 < groups_end) next = load_group(raw, (size_t)i + 32, pk);
+            // the lines two groups further on, into L1 (a group is 48 / 64 bytes)
+            if (i + 96 < groups_end) asm volatile("prefetch.global.L1 [%0];" ::"l"(raw + (pk ? 3 * (size_t)((i + 96) >> 1) : 2 * (size_t)(i + 96))));
+            float x[32];
+            unpack_group(cur, pk, x);
+            if (i == (int)begin) seg_start[k] = average;
+            if (i < (int)begin) {
+#pragma unroll
+                for (int j = 0; j < 32; j++) dc_step(average, x[j]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    float4 f;
+                    f.x = dc_step(average, x[j]);
+                    f.y = dc_step(average, x[j + 1]);
+                    f.z = dc_step(average, x[j + 2]);
+                    f.w = dc_step(average, x[j + 3]);
+                    *reinterpret_cast<float4 *>(filtered + i + j) = f;
+                }
+            }
+        }
+    }
+    // unaligned buffers and the call's tail: sample by sample
+    for (; i < end; i++) {
+        if (i == (int)begin) seg_start[k] = average;
+        const float v = dc_step(average, raw_sample(raw, (size_t)i, pk));
+        if (i >= (int)begin) filtered[i] = v;
+    }
+    seg_end[k] = average;
+}
+
+// every segment's guessed start against its predecessor's end (bit patterns)
+__global__ void airspy_check_kernel(int n_segments, const float *__restrict__ seg_start, const float *__restrict__ seg_end,
+                                    AirspyState *state)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x + 1;
+    if (k >= n_segments) return;
+    if ((long long)k * kSegment <= kWarmup) return;   // started from the true state at sample 0
+    if (__float_as_uint(seg_start[k]) != __float_as_uint(seg_end[k - 1])) atomicAdd(&state->mismatches, 1);
+}
+
+// commits the new average; after a mismatch (not seen in practice) redoes the stream sequentially from the carried state
+__global__ void airspy_commit_kernel(const uint8_t *__restrict__ raw, int n, int packed, int n_segments,
+                                     const float *__restrict__ seg_end, AirspyState *state, float *__restrict__ filtered,
+                                     int *__restrict__ total_mismatches)
+{
+    if (state->mismatches == 0) {
+        if (n_segments > 0) state->average = seg_end[n_segments - 1];
+        return;
+    }
+    float average = state->average;
+    for (int i = 0; i < n; i++) filtered[i] = dc_step(average, raw_sample(raw, (size_t)i, packed != 0));
+    state->average = average;
+    atomicAdd(total_mismatches, state->mismatches);
+    state->mismatches = 0;
+}
+
+// Four complex outputs per thread: the 56 filtered samples f[8t - 48 .. 8t + 7] they need come in through fourteen
+// 16-byte loads (f is 16-byte aligned and has kHistory + 1 older samples in front of it).
+__global__ void airspy_hilbert_kernel(const float *__restrict__ f, int n_pairs, const AirspyState *__restrict__ state,
+                                      float2 *__restrict__ out)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k0 = 4 * t;
+    if (k0 >= n_pairs) return;
+    float w[56];   // w[j] = f[8 t - 48 + j]
+    const float4 *src = reinterpret_cast<const float4 *>(f + 8 * (long long)t - 48);
+    const int have = min(4, n_pairs - k0);   // the call's last thread may own fewer than four pairs: do not read past them
+#pragma unroll
+    for (int q = 0; q < 14; q++) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (q < 12 || 2 * have > 4 * (q - 12)) v = __ldg(src + q);
+        w[4 * q] = v.x;
+        w[4 * q + 1] = v.y;
+        w[4 * q + 2] = v.z;
+        w[4 * q + 3] = v.w;
+    }
+    const int inverted = state->inverted;
+#pragma unroll
+    for (int p = 0; p < 4; p++) {
+        if (p < have) {
+            const int newest = 48 + 2 * p + 1;   // index in w of the second sample of pair k0 + p
+            float acc = 0.0f;
+#pragma unroll
+            for (int j = 0; j < 12; j++) {
+                const int x = 2 * j;
+                acc = __fadd_rn(acc, __fmul_rn(c_hilbert[j], __fsub_rn(w[newest - (kHistory - x)], w[newest - (x + 1)])));
+            }
+            const float centre = w[newest - 24];
+            const bool invert = ((inverted + k0 + p) & 1) != 0;
+            out[k0 + p] = invert ? make_float2(-centre, -acc) : make_float2(centre, acc);
+        }
+    }
+}
+
+// the last kHistory filtered samples of [history | this call] become the next call's history; flips the invert flag
+__global__ void airspy_carry_kernel(float *__restrict__ with_history, int n, AirspyState *state)
+{
+    __shared__ float keep[kHistory];
+    const int t = threadIdx.x;
+    if (t < kHistory) keep[t] = with_history[n + t];
+    __syncthreads();
+    if (t < kHistory) with_history[t] = keep[t];
+    if (t == 0) state->inverted = (state->inverted + n / 2) & 1;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------- converter object
+struct sdrgpu_airspy {
+    int device = 0;
+    int max_samples = 0;
+    int packed = 0;
+    cudaStream_t stream = nullptr;   // own stream of the stand-alone converter
+    AirspyState *d_state = nullptr;
+    float *d_filtered = nullptr;     // [1 pad | kHistory older samples | max_samples | 8 pad]
+    float *d_seg_start = nullptr, *d_seg_end = nullptr;
+    int *d_total_mismatches = nullptr;
+    uint8_t *d_raw = nullptr;        // staging for host input
+    float2 *d_iq = nullptr;          // staging for host output
+};
+
+namespace sdrgpu {
+
+sdrgpu_status airspy_create(sdrgpu_airspy **out, int max_samples)
+{
+    static bool coefficients_loaded[64] = {false};
+    auto *a = new sdrgpu_airspy();
+    cudaGetDevice(&a->device);
+    a->max_samples = max_samples;
+    const int segments = (max_samples + kSegment - 1) / kSegment + 1;
+    auto bail = [&](sdrgpu_status s) {
+        airspy_destroy(a);
+        return s;
+    };
+#define CHK(call)                                                                                                   \
+    do {                                                                                                            \
+        cudaError_t e__ = (call);                                                                                   \
+        if (e__ != cudaSuccess) return bail(fail(SDRGPU_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e__))); \
+    } while (0)
+    if (a->device < 64 && !coefficients_loaded[a->device]) {
+        float h[12];
+        for (int j = 0; j < 12; j++) h[j] = 2.0f * -fabsf(kHalfBandLeft[j]);
+        CHK(cudaMemcpyToSymbol(c_hilbert, h, sizeof(h)));
+        coefficients_loaded[a->device] = true;
+    }
+    CHK(cudaMalloc(&a->d_state, sizeof(AirspyState)));
+    CHK(cudaMemset(a->d_state, 0, sizeof(AirspyState)));
+    // + 1 in front (alignment of the 16-byte stores), + 8 behind (the Hilbert kernel's last 16-byte load)
+    CHK(cudaMalloc(&a->d_filtered, sizeof(float) * ((size_t)max_samples + kHistory + 1 + 8)));
+    CHK(cudaMemset(a->d_filtered, 0, sizeof(float) * ((size_t)max_samples + kHistory + 1 + 8)));
+    CHK(cudaMalloc(&a->d_seg_start, sizeof(float) * (size_t)segments));
+    CHK(cudaMalloc(&a->d_seg_end, sizeof(float) * (size_t)segments));
+    CHK(cudaMalloc(&a->d_total_mismatches, sizeof(int)));
+    CHK(cudaMemset(a->d_total_mismatches, 0, sizeof(int)));
+#undef CHK
+    *out = a;
+    return SDRGPU_OK;
+}
+
+void airspy_destroy(sdrgpu_airspy *a)
+{
+    if (!a) return;
+    cudaFree(a->d_state);
+    cudaFree(a->d_filtered);
+    cudaFree(a->d_seg_start);
+    cudaFree(a->d_seg_end);
+    cudaFree(a->d_total_mismatches);
+    cudaFree(a->d_raw);
+    cudaFree(a->d_iq);
+    if (a->stream) cudaStreamDestroy(a->stream);
+    delete a;
+}
+
+size_t airspy_raw_bytes(int n_samples, int packed) { return packed ? (size_t)(n_samples / 2) * 3 : (size_t)n_samples * 2; }
+
+// n_samples (even) raw real samples at d_raw -> n_samples / 2 complex samples at d_out, on `stream`
+sdrgpu_status airspy_enqueue(sdrgpu_airspy *a, const uint8_t *d_raw, int n_samples, int packed, float2 *d_out, cudaStream_t stream)
+{
+    if (n_samples == 0) return SDRGPU_OK;
+    if (n_samples > a->max_samples) return fail(SDRGPU_ERR_OVERFLOW, "%d samples exceed the converter's capacity %d", n_samples, a->max_samples);
+    const int segments = (n_samples + kSegment - 1) / kSegment;
+    float *f = a->d_filtered + kHistory + 1;   // + 1: float4 stores of the DC stage need 16-byte alignment
+    const int aligned = ((uintptr_t)d_raw & 15) == 0;
+    airspy_dc_kernel<<<(segments + 31) / 32, 32, 0, stream>>>(d_raw, n_samples, packed, aligned, a->d_state, f, a->d_seg_start, a->d_seg_end);
+    if (segments > 1) airspy_check_kernel<<<(segments + 255) / 256, 256, 0, stream>>>(segments, a->d_seg_start, a->d_seg_end, a->d_state);
+    airspy_commit_kernel<<<1, 1, 0, stream>>>(d_raw, n_samples, packed, segments, a->d_seg_end, a->d_state, f, a->d_total_mismatches);
+    const int pairs = n_samples / 2;
+    airspy_hilbert_kernel<<<((pairs + 3) / 4 + 127) / 128, 128, 0, stream>>>(f, pairs, a->d_state, d_out);
+    airspy_carry_kernel<<<1, 64, 0, stream>>>(a->d_filtered + 1, n_samples, a->d_state);
+    count_launch(segments > 1 ? 5 : 4);
+    SDRGPU_CUDA(cudaGetLastError());
+    return SDRGPU_OK;
+}
+
+sdrgpu_status airspy_reset(sdrgpu_airspy *a, cudaStream_t stream)
+{
+    SDRGPU_CUDA(cudaMemsetAsync(a->d_state, 0, sizeof(AirspyState), stream));
+    SDRGPU_CUDA(cudaMemsetAsync(a->d_filtered, 0, sizeof(float) * (kHistory + 1), stream));
+    return SDRGPU_OK;
+}
+
+}  // namespace sdrgpu
+
+extern "C" {
+
+sdrgpu_status sdrgpu_airspy_create(sdrgpu_airspy **out, int max_samples)
+{
+    if (!out || max_samples <= 0 || (max_samples & 1)) return fail(SDRGPU_ERR_INVALID_ARG, "max_samples must be positive and even");
+    *out = nullptr;
+    sdrgpu_airspy *a = nullptr;
+    SDRGPU_TRY(sdrgpu::airspy_create(&a, max_samples));
+    if (cudaStreamCreateWithFlags(&a->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        sdrgpu::airspy_destroy(a);
+        return fail(SDRGPU_ERR_CUDA, "cannot create a stream");
+    }
+    *out = a;
+    return SDRGPU_OK;
+}
+
+sdrgpu_status sdrgpu_airspy_destroy(sdrgpu_airspy *a)
+{
+    if (a) {
+        cudaSetDevice(a->device);
+        if (a->stream) cudaStreamSynchronize(a->stream);
+    }
+    sdrgpu::airspy_destroy(a);
+    return SDRGPU_OK;
+}
+
+sdrgpu_status sdrgpu_airspy_set_sample_packing(sdrgpu_airspy *a, int enabled)
+{
+    if (!a) return fail(SDRGPU_ERR_INVALID_ARG, "NULL handle");
+    a->packed = enabled != 0;
+    return SDRGPU_OK;
+}
+
+sdrgpu_status sdrgpu_airspy_convert(sdrgpu_airspy *a, const void *raw, int raw_mem, int n_samples, float *iq, int iq_mem)
+{
+    if (!a) return fail(SDRGPU_ERR_INVALID_ARG, "NULL handle");
+    if (n_samples < 0 || (n_samples & 1)) return fail(SDRGPU_ERR_INVALID_ARG, "n_samples must be even (two real samples per complex sample)");
+    if (n_samples > a->max_samples) return fail(SDRGPU_ERR_OVERFLOW, "%d samples exceed max_samples %d", n_samples, a->max_samples);
+    if (n_samples == 0) return SDRGPU_OK;
+    if (!raw || !iq) return fail(SDRGPU_ERR_INVALID_ARG, "NULL buffer");
+    SDRGPU_CUDA(cudaSetDevice(a->device));
+    const uint8_t *d_raw = reinterpret_cast<const uint8_t *>(raw);
+    const size_t bytes = sdrgpu::airspy_raw_bytes(n_samples, a->packed);
+    if (raw_mem == SDRGPU_HOST) {
+        if (!a->d_raw) SDRGPU_CUDA(cudaMalloc(&a->d_raw, sdrgpu::airspy_raw_bytes(a->max_samples, 0)));
+        SDRGPU_CUDA(cudaMemcpyAsync(a->d_raw, raw, bytes, cudaMemcpyHostToDevice, a->stream));
+        d_raw = a->d_raw;
+    }
+    float2 *d_out = reinterpret_cast<float2 *>(iq);
+    if (iq_mem == SDRGPU_HOST) {
+        if (!a->d_iq) SDRGPU_CUDA(cudaMalloc(&a->d_iq, sizeof(float2) * (size_t)(a->max_samples / 2)));
+        d_out = a->d_iq;
+    } else if ((uintptr_t)iq & 7) {
+        return fail(SDRGPU_ERR_INVALID_ARG, "device output must be 8-byte aligned");
+    }
+    SDRGPU_TRY(sdrgpu::airspy_enqueue(a, d_raw, n_samples, a->packed, d_out, a->stream));
+    if (iq_mem == SDRGPU_HOST)
+        SDRGPU_CUDA(cudaMemcpyAsync(iq, d_out, sizeof(float) * (size_t)n_samples, cudaMemcpyDeviceToHost, a->stream));
+    SDRGPU_CUDA(cudaStreamSynchronize(a->stream));
+    return SDRGPU_OK;
+}
+
+sdrgpu_status sdrgpu_airspy_mismatches(sdrgpu_airspy *a, int *count)
+{
+    if (!a || !count) return fail(SDRGPU_ERR_INVALID_ARG, "NULL argument");
+    SDRGPU_CUDA(cudaSetDevice(a->device));
+    SDRGPU_CUDA(cudaStreamSynchronize(a->stream));
+    SDRGPU_CUDA(cudaMemcpy(count, a->d_total_mismatches, sizeof(int), cudaMemcpyDeviceToHost));
+    return SDRGPU_OK;
+}
+
+}  // extern "C"

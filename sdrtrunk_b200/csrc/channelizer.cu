@@ -700,6 +700,7 @@ struct sdrgpu_channelizer {
     float2 *d_in = nullptr;    // staging for host input (float I/Q)
     uint8_t *d_raw = nullptr;  // staging for host input in a native tuner format
     int in_format = SDRGPU_FORMAT_F32;
+    sdrgpu_airspy *airspy = nullptr;   // SDRGPU_FORMAT_AIRSPY_*: the stateful raw-sample converter
     float *d_out = nullptr;    // staging for host output
     size_t d_out_bytes = 0;
     int n_sel = 0;
@@ -935,37 +936,49 @@ sdrgpu_status sdrgpu::chan_enqueue(sdrgpu_channelizer *h, const float2 *d_in, in
 
 cudaStream_t sdrgpu::chan_stream(const sdrgpu_channelizer *h) { return h->stream; }
 
-size_t sdrgpu::chan_value_bytes(const sdrgpu_channelizer *h)
+size_t sdrgpu::chan_complex_bytes(const sdrgpu_channelizer *h)
 {
-    return h->in_format == SDRGPU_FORMAT_F32 ? 4 : (h->in_format == SDRGPU_FORMAT_S16LE ? 2 : 1);
+    switch (h->in_format) {
+    case SDRGPU_FORMAT_F32: return 8;
+    case SDRGPU_FORMAT_S16LE: return 4;
+    case SDRGPU_FORMAT_AIRSPY_U16LE: return 4;       // two real samples of two bytes
+    case SDRGPU_FORMAT_AIRSPY_PACKED12: return 3;    // two real samples in three bytes
+    default: return 2;
+    }
 }
 
 sdrgpu_status sdrgpu::chan_upload(sdrgpu_channelizer *h, const void *iq, size_t first, int n, cudaStream_t copy_stream)
 {
-    const size_t vb = chan_value_bytes(h);
+    const size_t cb = chan_complex_bytes(h);
     if (!h->d_in) SDRGPU_CUDA(cudaMalloc(&h->d_in, sizeof(float2) * (size_t)h->max_in_complex));
     void *dst = h->d_in + first;
     if (h->in_format != SDRGPU_FORMAT_F32) {
-        if (!h->d_raw) SDRGPU_CUDA(cudaMalloc(&h->d_raw, 2 * vb * (size_t)h->max_in_complex));
-        dst = h->d_raw + 2 * vb * first;
+        // sized for the widest native format, so that the format can change without reallocating
+        if (!h->d_raw) SDRGPU_CUDA(cudaMalloc(&h->d_raw, 4 * (size_t)h->max_in_complex));
+        dst = h->d_raw + cb * first;
     }
-    SDRGPU_CUDA(cudaMemcpyAsync(dst, reinterpret_cast<const uint8_t *>(iq) + 2 * vb * first, 2 * vb * (size_t)n,
+    SDRGPU_CUDA(cudaMemcpyAsync(dst, reinterpret_cast<const uint8_t *>(iq) + cb * first, cb * (size_t)n,
                                 cudaMemcpyHostToDevice, copy_stream));
     return SDRGPU_OK;
 }
 
 const float2 *sdrgpu::chan_convert(sdrgpu_channelizer *h, const void *iq_device, size_t first, int n)
 {
-    const size_t vb = chan_value_bytes(h);
+    const size_t cb = chan_complex_bytes(h);
     if (h->in_format == SDRGPU_FORMAT_F32)
         return iq_device ? reinterpret_cast<const float2 *>(iq_device) + first : h->d_in + first;
     if (!h->d_in && cudaMalloc(&h->d_in, sizeof(float2) * (size_t)h->max_in_complex) != cudaSuccess) return nullptr;
     const uint8_t *src = iq_device ? reinterpret_cast<const uint8_t *>(iq_device) : h->d_raw;
-    if (n > 0) {
+    if (n > 0 && h->airspy) {
+        // two real samples per complex sample: unpack, DC removal, Hilbert transform (airspy.cu), in stream order
+        if (airspy_enqueue(h->airspy, src + cb * first, 2 * n, h->in_format == SDRGPU_FORMAT_AIRSPY_PACKED12, h->d_in + first,
+                           h->stream) != SDRGPU_OK)
+            return nullptr;
+    } else if (n > 0) {
         const size_t values = 2 * (size_t)n;
         int grid = (int)((values + 255) / 256);
         if (grid > 148 * 16) grid = 148 * 16;
-        convert_kernel<<<grid, 256, 0, h->stream>>>(h->in_format, src + 2 * vb * first, reinterpret_cast<float *>(h->d_in + first),
+        convert_kernel<<<grid, 256, 0, h->stream>>>(h->in_format, src + cb * first, reinterpret_cast<float *>(h->d_in + first),
                                                     values);
         count_launch();
     }
@@ -1101,6 +1114,7 @@ sdrgpu_status sdrgpu_chan_destroy(sdrgpu_channelizer *h)
     cudaFree(h->d_state[1]);
     cudaFree(h->d_in);
     cudaFree(h->d_raw);
+    sdrgpu::airspy_destroy(h->airspy);
     cudaFree(h->d_out);
     cudaFree(h->d_sel);
     cudaFree(h->d_gain_f);
@@ -1137,8 +1151,18 @@ sdrgpu_status sdrgpu_chan_sync(sdrgpu_channelizer *h)
 sdrgpu_status sdrgpu_chan_set_input_format(sdrgpu_channelizer *h, int format)
 {
     if (!h) return fail(SDRGPU_ERR_INVALID_ARG, "NULL handle");
-    if (format < SDRGPU_FORMAT_F32 || format > SDRGPU_FORMAT_S16LE) return fail(SDRGPU_ERR_INVALID_ARG, "unknown sample format %d", format);
+    if (format < SDRGPU_FORMAT_F32 || format > SDRGPU_FORMAT_AIRSPY_PACKED12)
+        return fail(SDRGPU_ERR_INVALID_ARG, "unknown sample format %d", format);
+    SDRGPU_CUDA(cudaSetDevice(h->device));
     SDRGPU_CUDA(cudaStreamSynchronize(h->stream));
+    const bool airspy = format == SDRGPU_FORMAT_AIRSPY_U16LE || format == SDRGPU_FORMAT_AIRSPY_PACKED12;
+    const bool was = h->in_format == SDRGPU_FORMAT_AIRSPY_U16LE || h->in_format == SDRGPU_FORMAT_AIRSPY_PACKED12;
+    if (airspy && !h->airspy) SDRGPU_TRY(sdrgpu::airspy_create(&h->airspy, 2 * h->max_in_complex));
+    if (!airspy && h->airspy) {   // a later return to the Airspy formats starts from a fresh converter
+        sdrgpu::airspy_destroy(h->airspy);
+        h->airspy = nullptr;
+    }
+    (void)was;   // switching between the two Airspy packings keeps the converter state (setSamplePacking)
     h->in_format = format;
     return SDRGPU_OK;
 }

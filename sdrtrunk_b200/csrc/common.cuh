@@ -50,8 +50,15 @@ cudaStream_t chan_stream(const sdrgpu_channelizer *h);
 // format is a native one.  chan_convert returns the device float2 pointer of the chunk.
 sdrgpu_status chan_upload(sdrgpu_channelizer *h, const void *iq, size_t first, int n, cudaStream_t copy_stream);
 const float2 *chan_convert(sdrgpu_channelizer *h, const void *iq_device_or_null, size_t first, int n);
-size_t chan_value_bytes(const sdrgpu_channelizer *h);
+size_t chan_complex_bytes(const sdrgpu_channelizer *h);   // bytes of one complex sample in the handle's input format
 int chan_half(const sdrgpu_channelizer *h);
+
+// Airspy raw-sample converter (airspy.cu), stand-alone (sdrgpu_airspy_*) and as a channelizer input format
+sdrgpu_status airspy_create(sdrgpu_airspy **out, int max_samples);
+void airspy_destroy(sdrgpu_airspy *a);
+size_t airspy_raw_bytes(int n_samples, int packed);
+sdrgpu_status airspy_enqueue(sdrgpu_airspy *a, const uint8_t *d_raw, int n_samples, int packed, float2 *d_out, cudaStream_t stream);
+sdrgpu_status airspy_reset(sdrgpu_airspy *a, cudaStream_t stream);
 
 inline void count_launch(int n = 1) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 

@@ -185,12 +185,17 @@ class ComplexPolyphaseChannelizerM2:
         return self._process(samples, samples_mem, out, out_mem, native.LAYOUT_CHANNELS, out_stride_floats)
 
     _FORMATS = {"f32": (native.FORMAT_F32, np.float32), "u8": (native.FORMAT_U8, np.uint8),
-                "s8": (native.FORMAT_S8, np.int8), "s16le": (native.FORMAT_S16LE, np.dtype("<i2"))}
+                "s8": (native.FORMAT_S8, np.int8), "s16le": (native.FORMAT_S16LE, np.dtype("<i2")),
+                "airspy": (native.FORMAT_AIRSPY_U16LE, np.dtype("<u2")),
+                "airspy_packed": (native.FORMAT_AIRSPY_PACKED12, np.uint8)}
 
     def setSampleFormat(self, fmt):
         """Native tuner sample format of the buffers given to receive / receiveChannels: 'f32' (default), 'u8'
-        (ByteSampleConverter), 's8' (SignedByteSampleConverter), 's16le' (ConversionUtils); converted on the device."""
+        (ByteSampleConverter), 's8' (SignedByteSampleConverter), 's16le' (ConversionUtils), 'airspy' / 'airspy_packed'
+        (AirspySampleConverter: 12-bit real samples, two per complex sample; uint16 values or packed bytes);
+        converted on the device."""
         code, self._dtype = self._FORMATS[fmt]
+        self._packed = fmt == "airspy_packed"
         native.check(native.lib().sdrgpu_chan_set_input_format(self._h, code))
 
     def setStream(self, cuda_stream):
@@ -214,7 +219,7 @@ class ComplexPolyphaseChannelizerM2:
         L = native.lib()
         if samples_mem == native.HOST:
             samples = np.ascontiguousarray(samples, dtype=getattr(self, "_dtype", np.float32))
-            n_floats = samples.size
+            n_floats = samples.size // 3 * 2 if getattr(self, "_packed", False) else samples.size
             in_ptr = native.ptr(samples)
         else:
             in_ptr, n_floats = native.ptr(samples[0]), int(samples[1])
@@ -259,6 +264,46 @@ class _SampleConverter:
         native.check(native.lib().sdrgpu_convert_samples(self.FORMAT, native.ptr(raw), native.HOST, n, native.ptr(out),
                                                          native.HOST))
         return out
+
+
+class AirspySampleConverter:
+    """J/source/tuner/airspy/AirspySampleConverter.java: raw 12-bit real samples -> DC removal -> Hilbert transform ->
+    interleaved I/Q, on the device (bit-exact; state carries from buffer to buffer as in the Java object)."""
+
+    def __init__(self, maxSamples=1 << 20, device=0):
+        native.init(device)
+        self._h = C.c_void_p()
+        self._max = int(maxSamples)
+        self._packed = False
+        native.check(native.lib().sdrgpu_airspy_create(C.byref(self._h), self._max))
+
+    def setSamplePacking(self, enabled):
+        self._packed = bool(enabled)
+        native.check(native.lib().sdrgpu_airspy_set_sample_packing(self._h, 1 if enabled else 0))
+
+    def convert(self, raw):
+        """raw: the native buffer's bytes (uint8).  Returns float32 interleaved I/Q, one float per real sample."""
+        raw = np.ascontiguousarray(raw, np.uint8)
+        n = raw.size // 3 * 2 if self._packed else raw.size // 2
+        out = np.empty(n, np.float32)
+        native.check(native.lib().sdrgpu_airspy_convert(self._h, native.ptr(raw), native.HOST, n, native.ptr(out), native.HOST))
+        return out
+
+    def mismatches(self):
+        c = C.c_int(0)
+        native.check(native.lib().sdrgpu_airspy_mismatches(self._h, C.byref(c)))
+        return c.value
+
+    def dispose(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            native.lib().sdrgpu_airspy_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.dispose()
+        except Exception:
+            pass
 
 
 class ByteSampleConverter(_SampleConverter):

@@ -15,7 +15,7 @@ HOST, DEVICE = 0, 1
 LAYOUT_RESULTS, LAYOUT_CHANNELS = 0, 1
 WINDOW_HAMMING, WINDOW_BLACKMAN = 0, 1
 DEMOD_NONE, DEMOD_FM, DEMOD_FM_SQUELCH, DEMOD_DQPSK_DECISION, DEMOD_DQPSK_GARDNER = 0, 1, 2, 3, 4
-FORMAT_F32, FORMAT_U8, FORMAT_S8, FORMAT_S16LE = 0, 1, 2, 3
+FORMAT_F32, FORMAT_U8, FORMAT_S8, FORMAT_S16LE, FORMAT_AIRSPY_U16LE, FORMAT_AIRSPY_PACKED12 = 0, 1, 2, 3, 4, 5
 PRESET_P25_C4FM, PRESET_P25_LSM, PRESET_P25_HDQPSK, PRESET_NBFM, PRESET_DMR = 0, 1, 2, 3, 4
 SYNC_NONE, SYNC_P25_PHASE1, SYNC_P25_PHASE2 = 0, 1, 2
 (SYNC_EVENT_NONE, SYNC_EVENT_SYNC, SYNC_EVENT_INVERSION_90_CW, SYNC_EVENT_INVERSION_90_CCW, SYNC_EVENT_INVERSION_180,
@@ -90,6 +90,11 @@ PROTOTYPES = {
     "sdrgpu_chan_set_stream": (C.c_int, [_vp, _vp]),
     "sdrgpu_chan_sync": (C.c_int, [_vp]),
     "sdrgpu_convert_samples": (C.c_int, [C.c_int, _vp, C.c_int, C.c_int, _vp, C.c_int]),
+    "sdrgpu_airspy_create": (C.c_int, [C.POINTER(_vp), C.c_int]),
+    "sdrgpu_airspy_destroy": (C.c_int, [_vp]),
+    "sdrgpu_airspy_set_sample_packing": (C.c_int, [_vp, C.c_int]),
+    "sdrgpu_airspy_convert": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, C.c_int]),
+    "sdrgpu_airspy_mismatches": (C.c_int, [_vp, C.POINTER(C.c_int)]),
     "sdrgpu_chan_set_input_format": (C.c_int, [_vp, C.c_int]),
     "sdrgpu_chan_set_sample_rate": (C.c_int, [_vp, C.c_double]),
     "sdrgpu_chan_select": (C.c_int, [_vp, C.POINTER(OutputChannel), C.c_int, _f32p, C.c_int]),

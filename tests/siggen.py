@@ -142,3 +142,26 @@ def dibits_with_sync(rng, n_symbols, pattern, n_bits, first=40, period=180):
     for k in range(first, n_symbols - s.size, period):
         d[k:k + s.size] = s
     return d
+
+
+def airspy_raw(x, packed=False):
+    """real samples in [-1, 1) -> the Airspy's native buffer bytes: unsigned 12-bit, two bytes per sample little
+    endian, or "sample packing" (two samples in three bytes, AirspySampleConverter.convertPacked)"""
+    v = np.clip(np.round(np.asarray(x) * 2048.0) + 2048, 0, 4095).astype(np.uint32)
+    if not packed:
+        return v.astype("<u2").view(np.uint8)
+    a, b = v[0::2], v[1::2]
+    out = np.zeros(a.size * 3, np.uint8)
+    out[0::3] = a >> 4
+    out[1::3] = ((a & 0xF) << 4) | (b >> 8)
+    out[2::3] = b & 0xFF
+    return out
+
+
+def airspy_real_signal(rng, n, tones, fs=20e6, dc=0.01, noise=1e-3):
+    """real ADC stream: the complex band (fs/2 wide) sits around fs/4; tones = [(offset_hz, amplitude)]"""
+    t = np.arange(n)
+    x = dc + noise * rng.standard_normal(n)
+    for f, a in tones:
+        x = x + a * np.cos(2 * np.pi * (fs / 4 + f) * t / fs + rng.uniform(0, 2 * np.pi))
+    return x

@@ -248,3 +248,68 @@ def test_native_tuner_sample_formats(gpu, fmt):
     ref = ComplexPolyphaseChannelizerM2(taps, 25000 * m, m).receive(want_f)       # same kernels on converted floats
     assert np.array_equal(got, ref)
     assert sg.rel_rms(got, oracle.Channelizer(taps, m).receive(want_f, mode="f64")) < TOL
+
+
+# ------------------------------------------------------------------------------------------------ Airspy raw samples
+@pytest.mark.parametrize("packed", [False, True])
+def test_airspy_sample_converter_bit_exact(gpu, packed):
+    """AirspySampleConverter on the device: unpack + DCRemovalFilter + HilbertTransform, every float equal to the
+    oracle's.  The DC recursion is sequential; the device runs it speculatively per 4 096-sample segment and verifies,
+    so long buffers (many segments), short ones, odd cuts and a stream with a large DC step are all covered."""
+    from sdrtrunk_b200.dsp import AirspySampleConverter
+    rng = np.random.default_rng(5 + packed)
+    n = 300000
+    x = sg.airspy_real_signal(rng, n, [(1.3e6, 0.3), (-2.2e6, 0.1)], dc=0.03)
+    x[150000:] += 0.2                                     # DC jump in the middle of the stream
+    raw = sg.airspy_raw(x, packed)
+    bps = 3 if packed else 4                              # bytes per pair of samples
+    ref = oracle.AirspySampleConverter()
+    ref.setSamplePacking(packed)
+    conv = AirspySampleConverter(maxSamples=1 << 18)
+    conv.setSamplePacking(packed)
+    pos = 0
+    for pairs in (100000, 1, 23, 3000, 2048, 2049, 0, 40000):       # in pairs of samples
+        chunk = raw[bps * pos:bps * (pos + pairs)]
+        got, want = conv.convert(chunk), ref.convert(chunk)
+        assert got.size == want.size == 2 * pairs
+        assert np.array_equal(got, want), (pairs, np.nonzero(got != want)[0][:4])
+        pos += pairs
+    assert conv.mismatches() == 0                         # every speculative segment start was right
+
+
+def test_airspy_speculation_fallback_is_exact(gpu):
+    """A pathological stream defeats the speculation: with constant samples the recursion stalls half an ulp short of
+    its fixed point, on the side it came from.  The true average comes down from 0.9 and stalls just above 0.75; a
+    segment that guesses 0 stalls just below and never meets it.  The verification must notice and the sequential
+    fallback must still give the Java's result."""
+    from sdrtrunk_b200.dsp import AirspySampleConverter
+    n = 4 * 4096 + 512
+    ref, conv = oracle.AirspySampleConverter(), AirspySampleConverter(maxSamples=1 << 16)
+    high, flat = sg.airspy_raw(np.full(n, 0.9)), sg.airspy_raw(np.full(n, 0.75))
+    assert np.array_equal(conv.convert(high), ref.convert(high))
+    for _ in range(3):
+        assert np.array_equal(conv.convert(flat), ref.convert(flat))
+    assert conv.mismatches() > 0
+
+
+def test_channelizer_takes_airspy_buffers(gpu):
+    """sdrgpu_chan_set_input_format(AIRSPY_*): raw buffers in, channels out = converter followed by the channelizer"""
+    from sdrtrunk_b200.dsp import ComplexPolyphaseChannelizerM2
+    m = 400
+    rng = np.random.default_rng(9)
+    n_complex = 40 * (m // 2)
+    x = sg.airspy_real_signal(rng, 2 * n_complex, [(25000.0 * 7 + 3000, 0.2), (-25000.0 * 30 - 1000, 0.1)], fs=20e6)
+    taps = oracle.sinc_m2_channelizer(25000.0, m, 9)
+    for packed in (False, True):
+        raw = sg.airspy_raw(x, packed)
+        ref = oracle.AirspySampleConverter()
+        ref.setSamplePacking(packed)
+        iq = ref.convert(raw)
+        plain = ComplexPolyphaseChannelizerM2(taps, 25000 * m, m)
+        want = np.concatenate([plain.receive(iq[:2 * 3000]), plain.receive(iq[2 * 3000:])])
+        ch = ComplexPolyphaseChannelizerM2(taps, 25000 * m, m)
+        ch.setSampleFormat("airspy_packed" if packed else "airspy")
+        values = raw if packed else raw.view("<u2")
+        cut = 3000 * (3 if packed else 2)                 # 3000 complex samples
+        got = np.concatenate([ch.receive(values[:cut]), ch.receive(values[cut:])])
+        assert np.array_equal(got, want)

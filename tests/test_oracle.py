@@ -293,3 +293,26 @@ def test_inversion_feedback_recovers_a_falsely_locked_loop(offset, event):
         m = min(got.size, truth.size) - 8
         assert np.mean(got[:m] == truth[:m]) > 0.99                           # decodes the payload afterwards
         assert np.mean(plain[first + 40 + lag:][:m] == truth[:m]) < 0.5       # which the uncorrected loop never does
+
+
+# ------------------------------------------------------------------------------------------------ Airspy converter
+def test_airspy_converter_oracle_properties():
+    """real -> complex: a tone at fs/4 + f comes out at -f (the converter's fs/4 + fs/2 translation inverts the
+    spectrum; parity means reproducing that), DC is removed, packed and unpacked buffers give identical results, and
+    the result does not depend on how the stream is cut into buffers."""
+    rng = np.random.default_rng(0)
+    n = 200000
+    x = sg.airspy_real_signal(rng, n, [(1.3e6, 0.4)], dc=0.02)
+    un, pk = sg.airspy_raw(x), sg.airspy_raw(x, packed=True)
+    iq = oracle.AirspySampleConverter().convert(un)
+    z = iq[0::2] + 1j * iq[1::2]
+    spec = np.abs(np.fft.fft(z[5000:5000 + 65536] * np.hanning(65536))) / 32768
+    k = int(np.argmax(spec))
+    assert abs((k if k < 32768 else k - 65536) * 10e6 / 65536 + 1.3e6) < 400 and 0.36 < spec[k] < 0.42
+    assert spec[0] < 1e-4
+    c = oracle.AirspySampleConverter()
+    c.setSamplePacking(True)
+    assert np.array_equal(c.convert(pk), iq)
+    c = oracle.AirspySampleConverter()
+    parts = [c.convert(un[:2 * 1000]), c.convert(un[2 * 1000:2 * 1046]), c.convert(un[2 * 1046:2 * 1048]), c.convert(un[2 * 1048:])]
+    assert np.array_equal(np.concatenate(parts), iq)
