@@ -195,7 +195,7 @@ class Pipeline:
         bank = self.bank
         if samples_mem == native.HOST:
             samples = np.ascontiguousarray(samples, dtype=getattr(self.channelizer, "_dtype", np.float32))
-            n_floats = samples.size
+            n_floats = samples.size // 3 * 2 if getattr(self.channelizer, "_packed", False) else samples.size
             in_ptr = native.ptr(samples)
         else:
             in_ptr = native.ptr(samples)

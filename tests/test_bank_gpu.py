@@ -394,6 +394,39 @@ def test_pipeline_channelizer_to_c4fm_bank(gpu):
         assert np.array_equal(got[i][200:], want_full[200:]), k
 
 
+@pytest.mark.parametrize("packed", [False, True])
+def test_pipeline_from_airspy_native_buffers(gpu, packed):
+    """Airspy raw buffers -> (unpack, DC removal, Hilbert) -> channelizer -> C4FM bank, all on the device and chunked
+    through host buffers, equals the same pipeline fed the oracle converter's float I/Q."""
+    from sdrtrunk_b200.dsp import Bank, ComplexPolyphaseChannelizerM2, Pipeline
+    m, fs = 96, 2.4e6
+    rng = np.random.default_rng(19)
+    n_ch = 4 * 1024
+    n_real = 2 * (n_ch * m // 2)
+    real = sg.airspy_real_signal(rng, n_real, [(25000.0 * 3 + 500, 0.2), (-25000.0 * 20, 0.1)], fs=2 * fs, noise=0.05)
+    raw = sg.airspy_raw(real, packed)
+    ref = oracle.AirspySampleConverter()
+    ref.setSamplePacking(packed)
+    iq = ref.convert(raw)
+    taps, fir, bins = oracle.sinc_m2_channelizer(25000.0, m, 9), c4fm_taps(), [3, 17, 76]
+
+    def build(fmt):
+        chan = ComplexPolyphaseChannelizerM2(taps, int(fs), m)
+        chan.setChannels(bins)
+        chan.setSampleFormat(fmt)
+        bank = Bank.preset(gpu.PRESET_P25_C4FM, len(bins), 50000.0, fir, max_samples_per_call=n_ch)
+        return Pipeline(chan, bank)
+
+    want = build("f32").process(iq)
+    pipe = build("airspy_packed" if packed else "airspy")
+    values = raw if packed else raw.view("<u2")
+    cut = (n_real // 3 // 2 * 2) * (3 if packed else 2) // 2          # an even number of samples into the stream
+    got = [np.concatenate(parts) for parts in zip(pipe.process(values[:cut]), pipe.process(values[cut:]))]
+    for a, b in zip(got, want):
+        assert a.size == b.size and a.size > 300
+        assert np.array_equal(a, b)
+
+
 def test_config1_nbfm_chain(gpu):
     """BASELINE configs[0] / SURVEY 8d config 1: 2.4 MS/s -> channelizer M = 96 -> bin 4 (50 kHz) -> ComplexDecimateX2
     -> 25 kHz -> 45-tap low-pass -> squelching FM discriminator, fused on the device, against the oracle chain.
