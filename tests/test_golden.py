@@ -54,7 +54,35 @@ def test_oracle_reproduces_filter_fm_chain_golden():
     assert np.array_equal(oracle.convert_samples(c["raw16"].tobytes(), "s16le"), c["s16le"])
 
 
+def test_oracle_reproduces_airspy_and_sync_golden():
+    g = load("airspy_sync.npz")
+    c = oracle.AirspySampleConverter()
+    assert np.array_equal(c.convert(g["raw_unpacked"]), g["iq"])
+    c = oracle.AirspySampleConverter()
+    c.setSamplePacking(True)
+    assert np.array_equal(c.convert(g["raw_packed"]), g["iq"])
+    chain = oracle.P25Chain(oracle.C4FM, 50000.0, g["sync_fir"])
+    chain.attach_sync(oracle.SYNC_P25_PHASE1, 50000.0)
+    sym = chain.receive(g["sync_x"])
+    assert np.array_equal(sym, g["sync_symbols"])
+    events = (sym >> 2) & 7
+    assert events[events > 0][0] == oracle.SYNC_EVENT_90_CW and np.count_nonzero(events == oracle.SYNC_EVENT_SYNC) >= 4
+
+
 # ------------------------------------------------------------------------------------------------ CUDA vs golden
+@pytest.mark.gpu
+def test_cuda_airspy_and_sync_match_golden(gpu):
+    from sdrtrunk_b200.dsp import AirspySampleConverter, Bank
+    g = load("airspy_sync.npz")
+    for packed, key in ((False, "raw_unpacked"), (True, "raw_packed")):
+        c = AirspySampleConverter(maxSamples=8192)
+        c.setSamplePacking(packed)
+        assert np.array_equal(c.convert(g[key]), g["iq"])
+    bank = Bank.preset(gpu.PRESET_P25_C4FM, 1, 50000.0, g["sync_fir"], max_samples_per_call=g["sync_x"].size // 2)
+    bank.setSyncDetector(gpu.SYNC_P25_PHASE1)
+    assert np.array_equal(bank.process(g["sync_x"].reshape(1, -1))[0], g["sync_symbols"])
+
+
 @pytest.mark.gpu
 def test_cuda_channelizer_matches_golden(gpu):
     from sdrtrunk_b200.dsp import ComplexPolyphaseChannelizerM2, FilterFactory

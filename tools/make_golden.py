@@ -71,6 +71,20 @@ def main():
     raw16 = rng.integers(-32768, 32768, 256).astype("<i2")
     np.savez_compressed(os.path.join(OUT, "converters.npz"), raw8=raw8, raw16=raw16, u8=oracle.convert_samples(raw8.tobytes(), "u8"),
                         s8=oracle.convert_samples(raw8.tobytes(), "s8"), s16le=oracle.convert_samples(raw16.tobytes(), "s16le"))
+    # ---- Airspy native buffers and the on-device sync detector (own seed: the vectors above stay as they are)
+    rng2 = np.random.default_rng(20240102)
+    real = sg.airspy_real_signal(rng2, 6000, [(1.1e6, 0.3), (-2.7e6, 0.15)], dc=0.02)
+    raw_u = sg.airspy_raw(real)
+    raw_p = sg.airspy_raw(real, packed=True)
+    conv = oracle.AirspySampleConverter()
+    iq = np.concatenate([conv.convert(raw_u[:2 * 2500]), conv.convert(raw_u[2 * 2500:])])
+    dib = sg.dibits_with_sync(rng2, 1200, sg.P25_PHASE1_SYNC, 48)
+    nn = 12 * 1024
+    xs = sg.interleave(sg.c4fm(dib, carrier_offset=-1250.0, timing_phase=0.4, n_samples=nn, amplitude=0.5) + sg.awgn(rng2, nn, 0.01))
+    chain = oracle.P25Chain(oracle.C4FM, 50000.0, fir)
+    chain.attach_sync(oracle.SYNC_P25_PHASE1, 50000.0)
+    np.savez_compressed(os.path.join(OUT, "airspy_sync.npz"), raw_unpacked=raw_u, raw_packed=raw_p, iq=iq, sync_x=xs, sync_fir=fir,
+                        sync_symbols=chain.receive(xs))
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 
