@@ -100,7 +100,7 @@ sdrgpu_status sdrgpu_convert_samples(int format, const void *src, int src_mem, i
 /* AirspySampleConverter (J/source/tuner/airspy/AirspySampleConverter.java:27-158): unpack -> DCRemovalFilter(0.01f)
  * (J/dsp/filter/dc/DCRemovalFilter.java:52-67) -> HilbertTransform.filter (J/dsp/filter/hilbert/HilbertTransform.java:
  * 88-132, coefficients from Filters.HALF_BAND_FILTER_47T).  Bit-exact with the Java: the sequential DC recursion is
- * run speculatively in 4 096-sample segments and verified (airspy.cu).  State (DC average, the Hilbert filter's last 47
+ * run speculatively in 2 048-sample segments and verified (airspy.cu).  State (DC average, the Hilbert filter's last 47
  * samples, the fs/2 sign) carries over from call to call as in the Java object. */
 typedef struct sdrgpu_airspy sdrgpu_airspy;
 sdrgpu_status sdrgpu_airspy_create(sdrgpu_airspy **a, int max_samples);   /* real samples per call, even */
@@ -108,7 +108,10 @@ sdrgpu_status sdrgpu_airspy_destroy(sdrgpu_airspy *a);
 sdrgpu_status sdrgpu_airspy_set_sample_packing(sdrgpu_airspy *a, int enabled);   /* AirspySampleConverter.setSamplePacking */
 /* n_samples (even) raw samples -> n_samples floats of interleaved I/Q (n_samples / 2 complex samples) */
 sdrgpu_status sdrgpu_airspy_convert(sdrgpu_airspy *a, const void *raw, int raw_mem, int n_samples, float *iq, int iq_mem);
-/* diagnostics: segments whose speculative start had to be redone sequentially since creation (expected 0) */
+/* diagnostics since creation: segments redone in parallel because their speculative start had not merged yet
+ * (slowly varying input), and segments still inconsistent after that, which made a call fall back to one sequential
+ * thread (noiseless constant / periodic input; expected 0 with ADC noise present) */
+sdrgpu_status sdrgpu_airspy_repaired(sdrgpu_airspy *a, int *count);
 sdrgpu_status sdrgpu_airspy_mismatches(sdrgpu_airspy *a, int *count);
 
 /* ------------------------------------------------------------------ polyphase channelizer

@@ -10,8 +10,10 @@
 // cut into 2 048-sample segments, one thread each; a thread starts 4 096 samples early from a guessed average of 0,
 // and a second kernel checks that the value every segment arrived at on its first sample equals the value its
 // predecessor ended on.  If all checks hold -- they do unless the input is pathological -- the outputs are exactly
-// the sequential ones by induction from segment 0, which starts from the true carried state.  Otherwise a single
-// thread redoes the call's samples from the carried state (correct, slow, never seen in practice).
+// the sequential ones by induction from segment 0, which starts from the true carried state.  Segments that fail the
+// check (slowly varying inputs can need ~4 000 samples to merge) are redone in parallel from their predecessor's end,
+// twice; only if the check still fails -- noiseless periodic or constant inputs never merge -- a single thread redoes
+// the call's samples from the carried state (correct, slow, not seen with ADC noise present).
 //
 // The Hilbert transform is a plain FIR once the Java's circular buffer + index map are unrolled (checked against
 // the literal restatement in oracle/orc_airspy.c): with n the second sample of pair k,
@@ -28,6 +30,7 @@ namespace {
 
 constexpr int kSegment = 2048;   // samples per thread of the DC stage (more, shorter segments: more warps to hide latency)
 constexpr int kWarmup = 4096;    // samples a thread runs ahead of its segment from the guessed state
+constexpr int kRepairRounds = 2; // parallel repairs of late-merging segments before the sequential fallback
 constexpr int kHistory = 47;     // HilbertTransform: the filter length; ages 1 .. 47 behind the newest sample
 constexpr float kRatio = 0.01f;  // AirspySampleConverter.java:31
 
@@ -173,7 +176,30 @@ __global__ void __launch_bounds__(32) airspy_dc_kernel(const uint8_t *__restrict
     seg_end[k] = average;
 }
 
-// every segment's guessed start against its predecessor's end (bit patterns)
+// Repair round: a segment whose start value differs from what its predecessor ended on (the guess had not merged with
+// the true trajectory yet -- slowly varying inputs can take ~4 000 samples) is redone from that value, without
+// warm-up.  Its new end almost always equals its old one (the runs merge inside the segment), so one round settles
+// it; if not, the next round moves on to the successor.  In-place and racy on purpose: whichever value of
+// seg_end[k - 1] a thread sees, it records the one it used in seg_start[k], and the check below accepts the result
+// only if every start equals its predecessor's end once all rounds are over.
+__global__ void __launch_bounds__(32) airspy_repair_kernel(const uint8_t *__restrict__ raw, int n, int packed, int n_segments,
+                                                             float *__restrict__ filtered, float *__restrict__ seg_start,
+                                                             float *__restrict__ seg_end, int *__restrict__ repaired)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x + 1;
+    if (k >= n_segments) return;
+    if ((long long)k * kSegment <= kWarmup) return;   // started from the true state at sample 0
+    const float truth = seg_end[k - 1];
+    if (__float_as_uint(seg_start[k]) == __float_as_uint(truth)) return;
+    const int begin = k * kSegment, end = min(n, begin + kSegment);
+    float average = truth;
+    for (int i = begin; i < end; i++) filtered[i] = dc_step(average, raw_sample(raw, (size_t)i, packed != 0));
+    seg_start[k] = truth;
+    seg_end[k] = average;
+    atomicAdd(repaired, 1);
+}
+
+// every segment's start against its predecessor's end (bit patterns)
 __global__ void airspy_check_kernel(int n_segments, const float *__restrict__ seg_start, const float *__restrict__ seg_end,
                                     AirspyState *state)
 {
@@ -259,7 +285,7 @@ struct sdrgpu_airspy {
     AirspyState *d_state = nullptr;
     float *d_filtered = nullptr;     // [1 pad | kHistory older samples | max_samples | 8 pad]
     float *d_seg_start = nullptr, *d_seg_end = nullptr;
-    int *d_total_mismatches = nullptr;
+    int *d_total_mismatches = nullptr, *d_repaired = nullptr;
     uint8_t *d_raw = nullptr;        // staging for host input
     float2 *d_iq = nullptr;          // staging for host output
 };
@@ -297,6 +323,8 @@ sdrgpu_status airspy_create(sdrgpu_airspy **out, int max_samples)
     CHK(cudaMalloc(&a->d_seg_end, sizeof(float) * (size_t)segments));
     CHK(cudaMalloc(&a->d_total_mismatches, sizeof(int)));
     CHK(cudaMemset(a->d_total_mismatches, 0, sizeof(int)));
+    CHK(cudaMalloc(&a->d_repaired, sizeof(int)));
+    CHK(cudaMemset(a->d_repaired, 0, sizeof(int)));
 #undef CHK
     *out = a;
     return SDRGPU_OK;
@@ -310,6 +338,7 @@ void airspy_destroy(sdrgpu_airspy *a)
     cudaFree(a->d_seg_start);
     cudaFree(a->d_seg_end);
     cudaFree(a->d_total_mismatches);
+    cudaFree(a->d_repaired);
     cudaFree(a->d_raw);
     cudaFree(a->d_iq);
     if (a->stream) cudaStreamDestroy(a->stream);
@@ -327,12 +356,17 @@ sdrgpu_status airspy_enqueue(sdrgpu_airspy *a, const uint8_t *d_raw, int n_sampl
     float *f = a->d_filtered + kHistory + 1;   // + 1: float4 stores of the DC stage need 16-byte alignment
     const int aligned = ((uintptr_t)d_raw & 15) == 0;
     airspy_dc_kernel<<<(segments + 31) / 32, 32, 0, stream>>>(d_raw, n_samples, packed, aligned, a->d_state, f, a->d_seg_start, a->d_seg_end);
-    if (segments > 1) airspy_check_kernel<<<(segments + 255) / 256, 256, 0, stream>>>(segments, a->d_seg_start, a->d_seg_end, a->d_state);
+    if (segments > 1) {
+        for (int round = 0; round < kRepairRounds; round++)
+            airspy_repair_kernel<<<(segments + 31) / 32, 32, 0, stream>>>(d_raw, n_samples, packed, segments, f, a->d_seg_start,
+                                                                          a->d_seg_end, a->d_repaired);
+        airspy_check_kernel<<<(segments + 255) / 256, 256, 0, stream>>>(segments, a->d_seg_start, a->d_seg_end, a->d_state);
+    }
     airspy_commit_kernel<<<1, 1, 0, stream>>>(d_raw, n_samples, packed, segments, a->d_seg_end, a->d_state, f, a->d_total_mismatches);
     const int pairs = n_samples / 2;
     airspy_hilbert_kernel<<<((pairs + 3) / 4 + 127) / 128, 128, 0, stream>>>(f, pairs, a->d_state, d_out);
     airspy_carry_kernel<<<1, 64, 0, stream>>>(a->d_filtered + 1, n_samples, a->d_state);
-    count_launch(segments > 1 ? 5 : 4);
+    count_launch(segments > 1 ? 5 + kRepairRounds : 4);
     SDRGPU_CUDA(cudaGetLastError());
     return SDRGPU_OK;
 }
@@ -414,6 +448,15 @@ sdrgpu_status sdrgpu_airspy_mismatches(sdrgpu_airspy *a, int *count)
     SDRGPU_CUDA(cudaSetDevice(a->device));
     SDRGPU_CUDA(cudaStreamSynchronize(a->stream));
     SDRGPU_CUDA(cudaMemcpy(count, a->d_total_mismatches, sizeof(int), cudaMemcpyDeviceToHost));
+    return SDRGPU_OK;
+}
+
+sdrgpu_status sdrgpu_airspy_repaired(sdrgpu_airspy *a, int *count)
+{
+    if (!a || !count) return fail(SDRGPU_ERR_INVALID_ARG, "NULL argument");
+    SDRGPU_CUDA(cudaSetDevice(a->device));
+    SDRGPU_CUDA(cudaStreamSynchronize(a->stream));
+    SDRGPU_CUDA(cudaMemcpy(count, a->d_repaired, sizeof(int), cudaMemcpyDeviceToHost));
     return SDRGPU_OK;
 }
 

@@ -290,8 +290,15 @@ class AirspySampleConverter:
         return out
 
     def mismatches(self):
+        """segments that forced a call onto the sequential fallback (see sdrgpu_airspy_mismatches)"""
         c = C.c_int(0)
         native.check(native.lib().sdrgpu_airspy_mismatches(self._h, C.byref(c)))
+        return c.value
+
+    def repaired(self):
+        """segments redone in parallel because their speculative start had not merged (sdrgpu_airspy_repaired)"""
+        c = C.c_int(0)
+        native.check(native.lib().sdrgpu_airspy_repaired(self._h, C.byref(c)))
         return c.value
 
     def dispose(self):

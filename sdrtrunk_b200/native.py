@@ -95,6 +95,7 @@ PROTOTYPES = {
     "sdrgpu_airspy_set_sample_packing": (C.c_int, [_vp, C.c_int]),
     "sdrgpu_airspy_convert": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, C.c_int]),
     "sdrgpu_airspy_mismatches": (C.c_int, [_vp, C.POINTER(C.c_int)]),
+    "sdrgpu_airspy_repaired": (C.c_int, [_vp, C.POINTER(C.c_int)]),
     "sdrgpu_chan_set_input_format": (C.c_int, [_vp, C.c_int]),
     "sdrgpu_chan_set_sample_rate": (C.c_int, [_vp, C.c_double]),
     "sdrgpu_chan_select": (C.c_int, [_vp, C.POINTER(OutputChannel), C.c_int, _f32p, C.c_int]),

@@ -277,6 +277,21 @@ def test_airspy_sample_converter_bit_exact(gpu, packed):
     assert conv.mismatches() == 0                         # every speculative segment start was right
 
 
+def test_airspy_late_merging_segments_are_repaired(gpu):
+    """A slow, noiseless square wave: guessed and true averages can need more than the 4 096-sample warm-up to become
+    bit-identical.  Such segments are redone in parallel from their predecessor's end; the result must be the Java's and
+    the sequential fallback must not be needed."""
+    from sdrtrunk_b200.dsp import AirspySampleConverter
+    n = 40 * 2048
+    t = np.arange(n)
+    x = 300.0 / 2048 * np.sign(np.sin(t * 0.001)) + 5.0 / 2048
+    raw = sg.airspy_raw(x)
+    ref, conv = oracle.AirspySampleConverter(), AirspySampleConverter(maxSamples=1 << 17)
+    for _ in range(3):
+        assert np.array_equal(conv.convert(raw), ref.convert(raw))
+    assert conv.mismatches() == 0
+
+
 def test_airspy_speculation_fallback_is_exact(gpu):
     """A pathological stream defeats the speculation: with constant samples the recursion stalls half an ulp short of
     its fixed point, on the side it came from.  The true average comes down from 0.9 and stalls just above 0.75; a
