@@ -263,7 +263,20 @@ sdrgpu_status sdrgpu_bank_reset_pll(sdrgpu_bank *b, int channel);
  * the event the detector raised at that symbol (syncDetected / correctInversion / syncLost) and, for
  * SDRGPU_SYNC_EVENT_SYNC, the number of bit errors passed to ISyncDetectListener.syncDetected.
  * Enabling (or re-enabling) starts from a fresh detector on every channel. */
-enum { SDRGPU_SYNC_NONE = 0, SDRGPU_SYNC_P25_PHASE1 = 1, SDRGPU_SYNC_P25_PHASE2 = 2 };
+enum { SDRGPU_SYNC_NONE = 0, SDRGPU_SYNC_P25_PHASE1 = 1, SDRGPU_SYNC_P25_PHASE2 = 2, SDRGPU_SYNC_P25_PHASE2_FRAMED = 3 };
+/* SDRGPU_SYNC_P25_PHASE2_FRAMED runs the reference's complete Phase 2 framing per channel instead of the bare
+ * detector: P25P2SuperFrameDetector (J/module/decode/p25/phase2/P25P2SuperFrameDetector.java:132-302), i.e. the
+ * fragment-sync state machine (sync patterns at dibits 360 and 540 of the 720-dibit fragment, 10 / 4 bit errors),
+ * its sync-loss accounting, and the P25P2SyncDetector with the PLL inversion detectors, fed -- as in the Java -- only
+ * while fragment sync is lost.  P25P2MessageFramer.receive hands every dibit to that class, so nothing is gated from
+ * outside and the result is exact.  Symbol bytes are then  dibit | events << 2  with the SDRGPU_P2_EVENT_* bits: the
+ * host cuts a super-frame fragment (the last 720 dibits) wherever SDRGPU_P2_EVENT_FRAGMENT is set. */
+enum {
+    SDRGPU_P2_EVENT_FRAGMENT = 1,      /* broadcastFragment */
+    SDRGPU_P2_EVENT_SYNC_LOSS = 2,     /* broadcastSyncLoss */
+    SDRGPU_P2_EVENT_INVERSION = 4,     /* correctInversion applied; bits 3-4: 1 = 90 CW, 2 = 90 CCW, 3 = 180 */
+    SDRGPU_P2_EVENT_SYNCHRONIZED = 32  /* mSynchronized after this dibit */
+};
 enum {
     SDRGPU_SYNC_EVENT_NONE = 0,
     SDRGPU_SYNC_EVENT_SYNC = 1,             /* primary pattern within 4 bit errors */

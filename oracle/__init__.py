@@ -102,6 +102,9 @@ def lib():
         "orc_sync_delay": (C.c_int, [vp]),
         "orc_sync_receive": (C.c_int, [vp, C.c_int, _f64p]),
         "orc_psk_attach_sync": (None, [vp, vp]),
+        "orc_p2_framer_create": (vp, [C.c_double]),
+        "orc_p2_framer_destroy": (None, [vp]),
+        "orc_p2_framer_receive": (C.c_int, [vp, C.c_int, _f64p]),
         "orc_p25_chain_attach_sync": (C.c_int, [vp, C.c_int, C.c_double]),
         "orc_psk_reset_pll": (None, [vp]),
         "orc_psk_get_state": (None, [vp, _f64p, _f64p, _f32p, _f32p]),
@@ -485,7 +488,8 @@ class AirspySampleConverter:
             self._h = None
 
 
-SYNC_P25_PHASE1, SYNC_P25_PHASE2 = 1, 2
+SYNC_P25_PHASE1, SYNC_P25_PHASE2, SYNC_P25_PHASE2_FRAMED = 1, 2, 3
+P2_EVENT_FRAGMENT, P2_EVENT_SYNC_LOSS, P2_EVENT_INVERSION, P2_EVENT_SYNCHRONIZED = 1, 2, 4, 32
 SYNC_EVENT_NONE, SYNC_EVENT_SYNC, SYNC_EVENT_90_CW, SYNC_EVENT_90_CCW, SYNC_EVENT_180, SYNC_EVENT_LOST = range(6)
 
 
@@ -509,6 +513,23 @@ class SyncDetector:
     def __del__(self):
         if getattr(self, "_h", None):
             lib().orc_sync_destroy(self._h)
+            self._h = None
+
+
+class P2SuperFrameDetector:
+    """P25P2SuperFrameDetector with its P25P2SyncDetector: receive(dibit) -> (event bits, PLL correction)."""
+
+    def __init__(self, sample_rate):
+        self._h = lib().orc_p2_framer_create(sample_rate)
+
+    def receive(self, dibit):
+        corr = C.c_double()
+        ev = lib().orc_p2_framer_receive(self._h, int(dibit), C.byref(corr))
+        return ev, corr.value
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orc_p2_framer_destroy(self._h)
             self._h = None
 
 

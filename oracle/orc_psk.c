@@ -59,6 +59,7 @@ struct orc_psk {
     cpx gardner_previous_symbol;
     cpx rot[4]; /* rotate-from +45, +135, -45, -135 */
     orc_sync *sync; /* optional dibit listener (not owned) */
+    orc_p2_framer *p2_framer;
 };
 
 orc_psk *orc_psk_create(int kind, double sample_rate, double symbol_rate, double pll_bandwidth, float sample_counter_gain)
@@ -108,6 +109,7 @@ void orc_psk_correct_inversion(orc_psk *p, double correction)
 }
 
 void orc_psk_attach_sync(orc_psk *p, orc_sync *s) { p->sync = s; }
+void orc_psk_attach_p2_framer(orc_psk *p, orc_p2_framer *f) { p->p2_framer = f; }
 
 /* CostasLoop.java:224-229 */
 void orc_psk_reset_pll(orc_psk *p)
@@ -291,6 +293,12 @@ int orc_psk_receive(orc_psk *p, const float *iq, int n_floats, uint8_t *dibits, 
                     orc_psk_correct_inversion(p, correction);
                 d |= event << 2;
             }
+            if (p->p2_framer) { /* P25P2MessageFramer.receive -> P25P2SuperFrameDetector.receive */
+                double correction = 0.0;
+                int event = orc_p2_framer_receive(p->p2_framer, d, &correction);
+                if (event & ORC_P2_EVENT_INVERSION) orc_psk_correct_inversion(p, correction);
+                d |= event << 2;
+            }
             dibits[n_symbols++] = (uint8_t)d;
         }
     }
@@ -323,6 +331,7 @@ struct orc_p25_chain {
     orc_psk *psk;
     float *tmp_a, *tmp_b;
     orc_sync *sync;
+    orc_p2_framer *p2_framer;
 };
 
 orc_p25_chain *orc_p25_chain_create(int kind, double sample_rate, const float *fir_taps, int n_taps)
@@ -349,7 +358,17 @@ orc_p25_chain *orc_p25_chain_create(int kind, double sample_rate, const float *f
 int orc_p25_chain_attach_sync(orc_p25_chain *c, int sync_kind, double sample_rate)
 {
     orc_sync_destroy(c->sync);
+    orc_p2_framer_destroy(c->p2_framer);
+    c->sync = NULL;
+    c->p2_framer = NULL;
+    if (sync_kind == ORC_SYNC_P25_PHASE2_FRAMED) {
+        c->p2_framer = orc_p2_framer_create(sample_rate);
+        orc_psk_attach_sync(c->psk, NULL);
+        orc_psk_attach_p2_framer(c->psk, c->p2_framer);
+        return 0;
+    }
     c->sync = orc_sync_create(sync_kind, sample_rate);
+    orc_psk_attach_p2_framer(c->psk, NULL);
     orc_psk_attach_sync(c->psk, c->sync);
     return c->sync ? 0 : -1;
 }
@@ -360,6 +379,7 @@ void orc_p25_chain_destroy(orc_p25_chain *c)
     orc_cfir_destroy(c->fir);
     orc_psk_destroy(c->psk);
     orc_sync_destroy(c->sync);
+    orc_p2_framer_destroy(c->p2_framer);
     free(c->tmp_a);
     free(c->tmp_b);
     free(c);

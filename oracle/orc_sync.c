@@ -115,3 +115,125 @@ int orc_sync_receive(orc_sync *s, int dibit, double *correction)
     }
     return event;
 }
+
+/* ---------------------------------------------------------------- APCO25 Phase 2 super-frame fragment detector
+ * J/module/decode/p25/phase2/P25P2SuperFrameDetector.java:53-70 (constants, buffers), 105-122 (syncDetected /
+ * syncLost), 132-168 (receive), 176-189 (broadcastFragment), 236-302 (checkFragmentSync), with its P25P2SyncDetector
+ * (fed only while not synchronized, through the 160-dibit delay buffer that keeps filling either way) and
+ * J/module/decode/p25/phase2/P25P2SyncPattern.java:25-57 (bit errors of 20 dibits against the sync pattern).
+ * P25P2MessageFramer.receive(Dibit) (:171-174) hands every dibit to this detector, so nothing is gated from outside:
+ * this is the reference's complete Phase 2 framing + PLL inversion feedback, statement for statement.  Not restated:
+ * what is done with a broadcast fragment (message parsing, scrambling-sequence updates) -- it does not feed back. */
+#define P2_FRAGMENT 720
+#define P2_DELAY 160
+
+struct orc_p2_framer {
+    orc_sync *detector;                 /* P25P2SyncDetector; its delay line is not used here */
+    uint8_t fragment[P2_FRAGMENT];      /* mFragmentBuffer */
+    int fragment_pointer;
+    uint8_t delay[P2_DELAY];            /* mSyncDetectionDelayBuffer */
+    int delay_pointer;
+    int dibits_processed;
+    int synchronized;
+    int event;                          /* events raised while the current dibit is processed */
+};
+
+orc_p2_framer *orc_p2_framer_create(double sample_rate)
+{
+    orc_p2_framer *f = (orc_p2_framer *)calloc(1, sizeof(*f));
+    f->detector = orc_sync_create(ORC_SYNC_P25_PHASE2, sample_rate);
+    return f;
+}
+
+void orc_p2_framer_destroy(orc_p2_framer *f)
+{
+    if (!f) return;
+    orc_sync_destroy(f->detector);
+    free(f);
+}
+
+/* DibitDelayBuffer.getBuffer(start, 20) + P25P2SyncPattern.getBitErrorCount */
+static int p2_sync_errors(const orc_p2_framer *f, int start)
+{
+    int pointer = (f->fragment_pointer + start) % P2_FRAGMENT;
+    uint64_t value = 0;
+    for (int x = 0; x < 20; x++) {
+        value = (value << 2) | f->fragment[pointer++];
+        if (pointer >= P2_FRAGMENT) pointer = 0;
+    }
+    /* per dibit: both bits wrong = 2 errors, one bit wrong = 1: the Hamming distance */
+    return __builtin_popcountll(value ^ 0x575D57F7FFull);
+}
+
+static void p2_broadcast_fragment(orc_p2_framer *f)
+{
+    if (f->dibits_processed > P2_FRAGMENT) f->event |= ORC_P2_EVENT_SYNC_LOSS;
+    f->dibits_processed = 0;
+    f->event |= ORC_P2_EVENT_FRAGMENT;
+}
+
+static void p2_check_fragment_sync(orc_p2_framer *f)
+{
+    if (f->dibits_processed <= 0) return;
+    if (f->synchronized) {
+        if (p2_sync_errors(f, 360) <= 10 && p2_sync_errors(f, 540) <= 10) {
+            p2_broadcast_fragment(f);
+            /* syncDetected(...) re-enters here with mDibitsProcessed == 0: nothing happens */
+        } else {
+            f->synchronized = 0;
+        }
+        return;
+    }
+    if (p2_sync_errors(f, 360) <= 4) {
+        f->synchronized = 1;
+        p2_broadcast_fragment(f);
+    } else {
+        f->synchronized = 1;
+        if (f->dibits_processed > P2_FRAGMENT - 180) f->event |= ORC_P2_EVENT_SYNC_LOSS;
+        f->dibits_processed = P2_FRAGMENT - 180;
+    }
+}
+
+int orc_p2_framer_receive(orc_p2_framer *f, int dibit, double *correction)
+{
+    if (correction) *correction = 0.0;
+    f->event = 0;
+    f->dibits_processed++;
+    f->fragment[f->fragment_pointer++] = (uint8_t)(dibit & 3);
+    if (f->fragment_pointer >= P2_FRAGMENT) f->fragment_pointer = 0;
+    if (f->synchronized) {
+        f->delay[f->delay_pointer++] = (uint8_t)(dibit & 3);
+        if (f->delay_pointer >= P2_DELAY) f->delay_pointer = 0;
+        if (f->dibits_processed >= P2_FRAGMENT) p2_check_fragment_sync(f);
+    } else {
+        int delayed = f->delay[f->delay_pointer];
+        f->delay[f->delay_pointer++] = (uint8_t)(dibit & 3);
+        if (f->delay_pointer >= P2_DELAY) f->delay_pointer = 0;
+        /* P25P2SyncDetector.receive -> MultiSyncPatternMatcher.receive: the matcher of orc_sync without its delay line */
+        orc_sync *s = f->detector;
+        s->bits = (s->bits << 1) & s->mask;
+        if (delayed & 2) s->bits += 1;
+        s->bits = (s->bits << 1) & s->mask;
+        if (delayed & 1) s->bits += 1;
+        s->bit_count += 2;
+        uint64_t difference = s->bits ^ s->pattern[0];
+        if (difference == 0 || __builtin_popcountll(difference) <= s->threshold) {
+            p2_check_fragment_sync(f); /* SoftSyncDetector -> P25P2SuperFrameDetector.syncDetected */
+            s->bit_count = 0;
+        }
+        for (int k = 0; k < 3; k++) {
+            if (s->bits == s->pattern[1 + k]) {
+                f->event |= ORC_P2_EVENT_INVERSION | ((k + 1) << 3);
+                if (correction) *correction = s->pll_correction[k];
+                s->bit_count = 0;
+            }
+        }
+        if (s->bit_count > s->sync_loss_threshold) s->bit_count = 0; /* syncLost: rebroadcast only */
+    }
+    if (f->dibits_processed > 3720) {
+        f->dibits_processed -= 3000;
+        f->event |= ORC_P2_EVENT_SYNC_LOSS;
+    }
+    if (f->synchronized) f->event |= ORC_P2_EVENT_SYNCHRONIZED;
+    return f->event;
+}

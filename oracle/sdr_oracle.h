@@ -181,7 +181,7 @@ void orc_psk_get_state(const orc_psk *p, double *phase, double *freq, float *sam
 int orc_pack_dibits(const uint8_t *dibits, int n, uint8_t *out);
 
 /* ---------------------------------------------------------------- sync detection + PLL inversion feedback (8f #3) */
-enum { ORC_SYNC_P25_PHASE1 = 1, ORC_SYNC_P25_PHASE2 = 2 };
+enum { ORC_SYNC_P25_PHASE1 = 1, ORC_SYNC_P25_PHASE2 = 2, ORC_SYNC_P25_PHASE2_FRAMED = 3 };
 /* event of one dibit: bits 0-2 one of these, bits 3-5 the primary detector's bit errors (SYNC only) */
 enum {
     ORC_SYNC_EVENT_NONE = 0,
@@ -196,6 +196,20 @@ orc_sync *orc_sync_create(int kind, double sample_rate);
 void orc_sync_destroy(orc_sync *s);
 int orc_sync_delay(const orc_sync *s);
 int orc_sync_receive(orc_sync *s, int dibit, double *correction);
+/* APCO25 Phase 2 super-frame fragment detector (P25P2SuperFrameDetector + its P25P2SyncDetector): the reference's
+ * complete Phase 2 framing and PLL inversion feedback.  Event bits of one dibit: */
+enum {
+    ORC_P2_EVENT_FRAGMENT = 1,      /* broadcastFragment: the last 720 dibits are a super-frame fragment */
+    ORC_P2_EVENT_SYNC_LOSS = 2,     /* broadcastSyncLoss was called */
+    ORC_P2_EVENT_INVERSION = 4,     /* correctInversion was called; bits 3-4: 1 = 90 CW, 2 = 90 CCW, 3 = 180 */
+    ORC_P2_EVENT_SYNCHRONIZED = 32  /* mSynchronized after this dibit */
+};
+typedef struct orc_p2_framer orc_p2_framer;
+orc_p2_framer *orc_p2_framer_create(double sample_rate);
+void orc_p2_framer_destroy(orc_p2_framer *f);
+int orc_p2_framer_receive(orc_p2_framer *f, int dibit, double *correction);
+void orc_psk_attach_p2_framer(orc_psk *p, orc_p2_framer *f);
+
 /* the demodulator then feeds every dibit to s (as the framer's listener does, synchronously after the PLL update of
  * that symbol), applies requested corrections with correctInversion and reports dibit | event << 2 per symbol */
 void orc_psk_attach_sync(orc_psk *p, orc_sync *s);
@@ -208,7 +222,8 @@ orc_p25_chain *orc_p25_chain_create(int kind, double sample_rate, const float *f
 void orc_p25_chain_destroy(orc_p25_chain *c);
 /* consumes whole 1024-complex-sample buffers only (the assembler framing); n_floats multiple of 2048 */
 int orc_p25_chain_receive(orc_p25_chain *c, const float *iq, int n_floats, uint8_t *dibits, float *agc_out);
-/* attaches a sync detector (owned by the chain) to the chain's demodulator */
+/* attaches a sync detector (owned by the chain) to the chain's demodulator; sync_kind ORC_SYNC_P25_PHASE2_FRAMED
+ * attaches the Phase 2 super-frame fragment detector instead */
 int orc_p25_chain_attach_sync(orc_p25_chain *c, int sync_kind, double sample_rate);
 
 #ifdef __cplusplus

@@ -309,6 +309,79 @@ def test_sync_detector_and_inversion_feedback_on_device(gpu, kind):
         bank2.setSyncDetector(7)
 
 
+def _p2_channel(rng, n, offset, holes=()):
+    """HDQPSK channel with the Phase 2 sync pattern every 180 symbols (every ISCH a sync ISCH), optional noise holes"""
+    n_sym = int(n * 6000 / 50000) + 8
+    dib = rng.integers(0, 4, n_sym).astype(np.uint8)
+    s = sg.sync_dibits(sg.P25_PHASE2_SYNC, 40)
+    for k in range(60, n_sym - 20, 180):
+        dib[k:k + 20] = s
+    z = sg.dqpsk(dib, symbol_rate=6000.0, carrier_offset=offset, timing_phase=rng.uniform(0, 1), n_samples=n, amplitude=0.5)
+    z = z + sg.awgn(rng, n, 0.01)
+    for a, ln in holes:
+        z[a:a + ln] = sg.awgn(rng, ln, 0.3)
+    return sg.interleave(z)
+
+
+def test_phase2_framing_on_device(gpu):
+    """SDRGPU_SYNC_P25_PHASE2_FRAMED: the reference's whole Phase 2 framing (P25P2SuperFrameDetector: fragment sync
+    state machine, sync-loss accounting, sync detector + PLL inversion feedback while unsynchronized) inside the
+    demodulator kernel: every byte (dibit | events << 2) equals the oracle's, through ragged calls, on channels that
+    lock rotated, lose the signal and re-acquire."""
+    from sdrtrunk_b200.dsp import Bank
+    preset, okind, taps = _preset(gpu, "hdqpsk")
+    rng = np.random.default_rng(41)
+    n = 40 * 1024
+    cases = [(0.0, ()), (1450.0, ()), (-1550.0, ()), (2900.0, ()), (80.0, ((15000, 12000),)), (0.0, ((0, n),))]
+    x = np.stack([_p2_channel(rng, n, off, holes) for off, holes in cases])
+    bank = Bank.preset(preset, len(cases), 50000.0, taps, max_samples_per_call=16 * 1024)
+    bank.setSyncDetector(gpu.SYNC_P25_PHASE2_FRAMED)
+    cuts = (0, 16384, 17000, 30000, n)
+    parts = [bank.process(x[:, 2 * a:2 * b]) for a, b in zip(cuts[:-1], cuts[1:])]
+    seen = 0
+    for k in range(len(cases)):
+        got = np.concatenate([p[k] for p in parts])
+        chain = oracle.P25Chain(okind, 50000.0, taps)
+        chain.attach_sync(oracle.SYNC_P25_PHASE2_FRAMED, 50000.0)
+        want = chain.receive(x[k])
+        assert got.size == want.size, k
+        assert np.array_equal(got, want), (k, np.nonzero(got != want)[0][:5])
+        ev = want >> 2
+        seen |= int(np.bitwise_or.reduce(ev))
+        frag = np.nonzero(ev & gpu.P2_EVENT_FRAGMENT)[0]
+        if k < 5:
+            assert frag.size >= 4 and np.all(np.diff(frag) >= 720), k      # fragments every 720 dibits while in sync
+        else:
+            assert frag.size == 0                                         # noise never frames
+        if k in (1, 2, 3):
+            assert np.any(ev & gpu.P2_EVENT_INVERSION), k                  # locked rotated, corrected on the device
+    assert seen & gpu.P2_EVENT_SYNC_LOSS and seen & gpu.P2_EVENT_SYNCHRONIZED
+
+
+def test_phase2_framing_thread_per_channel_kernel(gpu):
+    """the same through psk_wide_kernel (>= 3000 channels)"""
+    from sdrtrunk_b200.dsp import Bank
+    taps = hdqpsk_taps()
+    rng = np.random.default_rng(42)
+    n = 20 * 1024
+    cases = [(0.0, ()), (1450.0, ()), (-1550.0, ()), (30.0, ((8000, 6000),))]
+    base = np.stack([_p2_channel(rng, n, off, holes) for off, holes in cases])
+    c = 3072
+    x = np.tile(base, (c // len(cases), 1))
+    bank = Bank.preset(gpu.PRESET_P25_HDQPSK, c, 50000.0, taps, max_samples_per_call=n)
+    bank.setSyncDetector(gpu.SYNC_P25_PHASE2_FRAMED)
+    got = bank.process(x[:, :2 * 9 * 1024])
+    got2 = bank.process(x[:, 2 * 9 * 1024:])
+    want = []
+    for k in range(len(cases)):
+        chain = oracle.P25Chain(oracle.HDQPSK, 50000.0, taps)
+        chain.attach_sync(oracle.SYNC_P25_PHASE2_FRAMED, 50000.0)
+        want.append(chain.receive(base[k]))
+    assert all(np.any((w >> 2) & gpu.P2_EVENT_FRAGMENT) for w in want)
+    for k in range(c):
+        assert np.array_equal(np.concatenate([got[k], got2[k]]), want[k % len(cases)]), k
+
+
 def test_sync_detector_thread_per_channel_kernel(gpu):
     """the same through psk_wide_kernel (>= 3000 channels): six distinct channels tiled over 3072"""
     from sdrtrunk_b200.dsp import Bank

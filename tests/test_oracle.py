@@ -316,3 +316,127 @@ def test_airspy_converter_oracle_properties():
     c = oracle.AirspySampleConverter()
     parts = [c.convert(un[:2 * 1000]), c.convert(un[2 * 1000:2 * 1046]), c.convert(un[2 * 1046:2 * 1048]), c.convert(un[2 * 1048:])]
     assert np.array_equal(np.concatenate(parts), iq)
+
+
+# ------------------------------------------------------------------------------------------------ Phase 2 framing
+class _JavaSuperFrameDetector:
+    """P25P2SuperFrameDetector + P25P2SyncDetector restated independently of orc_sync.c: explicit circular buffers with
+    getBuffer(start, 20) views, per-dibit error counting as in P25P2SyncPattern, listener recursion kept."""
+    SYNC = [1, 1, 1, 3, 1, 1, 3, 1, 1, 1, 1, 3, 3, 3, 1, 3, 3, 3, 3, 3]
+    PATTERNS = (0x575D57F7FF, 0x0104015155, 0xFEFBFEAEAA, 0xA8A2A80800)
+
+    def __init__(self):
+        self.fragment, self.fp = [0] * 720, 0
+        self.delay, self.dp = [0] * 160, 0
+        self.processed, self.synchronized = 0, False
+        self.bits, self.count = 0, 0
+        self.event = 0
+
+    def _errors(self, start):
+        p = (self.fp + start) % 720
+        n = 0
+        for x in range(20):
+            mask = self.SYNC[x] ^ self.fragment[p]
+            n += 2 if mask == 3 else (1 if mask else 0)
+            p = (p + 1) % 720
+        return n
+
+    def _broadcast_fragment(self):
+        if self.processed > 720:
+            self.event |= 2
+        self.processed = 0
+        self.event |= 1
+
+    def _sync_detected(self):
+        self._check()
+
+    def _check(self):
+        if self.processed > 0:
+            if self.synchronized:
+                if self._errors(360) <= 10:
+                    if self._errors(540) <= 10:
+                        self._broadcast_fragment()
+                        self._sync_detected()
+                        return
+                    self.synchronized = False
+                    return
+                self.synchronized = False
+                return
+            if self._errors(360) <= 4:
+                self.synchronized = True
+                self._broadcast_fragment()
+            else:
+                self.synchronized = True
+                if self.processed > 540:
+                    self.event |= 2
+                self.processed = 540
+
+    def receive(self, dibit):
+        self.event = 0
+        self.processed += 1
+        self.fragment[self.fp] = dibit
+        self.fp = (self.fp + 1) % 720
+        if self.synchronized:
+            self.delay[self.dp] = dibit
+            self.dp = (self.dp + 1) % 160
+            if self.processed >= 720:
+                self._check()
+        else:
+            delayed = self.delay[self.dp]
+            self.delay[self.dp] = dibit
+            self.dp = (self.dp + 1) % 160
+            for bit in (delayed >> 1, delayed & 1):
+                self.bits = ((self.bits << 1) & ((1 << 40) - 1)) + bit
+            self.count += 2
+            if bin(self.bits ^ self.PATTERNS[0]).count("1") <= 4:
+                self._sync_detected()
+                self.count = 0
+            for k in (1, 2, 3):
+                if self.bits == self.PATTERNS[k]:
+                    self.event |= 4 | (k << 3)
+                    self.count = 0
+            if self.count > 1440:
+                self.count = 0
+        if self.processed > 3720:
+            self.processed -= 3000
+            self.event |= 2
+        return self.event | (32 if self.synchronized else 0)
+
+
+def _p2_dibits(rng, n, first=100, holes=(), bad=()):
+    """random dibits with the Phase 2 sync pattern every 180 dibits; `holes` = (start, length) stretches of pure
+    noise, `bad` = indexes of sync patterns that get 6 bit errors"""
+    d = rng.integers(0, 4, n).astype(np.uint8)
+    s = sg.sync_dibits(sg.P25_PHASE2_SYNC, 40)
+    for i, k in enumerate(range(first, n - 20, 180)):
+        v = sg.P25_PHASE2_SYNC
+        if i in bad:
+            for b in rng.choice(40, 6, replace=False):
+                v ^= 1 << int(b)
+        d[k:k + 20] = sg.sync_dibits(v, 40) if i in bad else s
+    for a, ln in holes:
+        d[a:a + ln] = rng.integers(0, 4, ln)
+    return d
+
+
+def test_phase2_super_frame_detector():
+    rng = np.random.default_rng(12)
+    n = 14000
+    d = _p2_dibits(rng, n, holes=((3000, 1500), (9000, 4200)), bad=(30, 31, 40))
+    rot = {0: 1, 1: 3, 3: 2, 2: 0}
+    d[5200:8000] = [rot[int(v)] for v in d[5200:8000]]          # a stretch received 90 degrees rotated
+    det, ref = oracle.P2SuperFrameDetector(50000.0), _JavaSuperFrameDetector()
+    events = []
+    for x in d:
+        ev, corr = det.receive(x)
+        assert ev == ref.receive(int(x))
+        assert (corr != 0.0) == bool(ev & oracle.P2_EVENT_INVERSION)
+        events.append(ev)
+    events = np.array(events)
+    frag = np.nonzero(events & oracle.P2_EVENT_FRAGMENT)[0]
+    assert frag.size >= 8 and np.all(np.isin(np.diff(frag), (720,)) | (np.diff(frag) > 720))
+    assert frag[0] == 100 + 19 + 160 + 180                      # misaligned first detection, then one ISCH later
+    sync = (events & oracle.P2_EVENT_SYNCHRONIZED) != 0
+    assert not sync[:279].any() and sync[279:2999].all() and not sync[3500:4400].all()
+    assert np.any(events & oracle.P2_EVENT_SYNC_LOSS)
+    assert np.any((events >> 3) & 3)                            # a rotated sync pattern was seen while unsynchronized
