@@ -286,6 +286,12 @@ enum {
     SDRGPU_SYNC_EVENT_LOST = 5              /* MultiSyncPatternMatcher: more than the loss threshold of bits without a match */
 };
 sdrgpu_status sdrgpu_bank_set_sync_detector(sdrgpu_bank *b, int kind);
+/* Tuning: how many lanes of a warp work on one channel in the symbol demodulator kernel -- 32 (one warp per channel),
+ * 16 (two channels per warp), 1 (one thread per channel), 0 = chosen from the bank size (default).  All variants do
+ * the same arithmetic on the same per-channel state; the result does not depend on the choice, which may change
+ * between calls -- except while a sync detector (SDRGPU_SYNC_P25_PHASE1 / _PHASE2) is enabled: choose the layout first
+ * (SDRGPU_ERR_BAD_STATE otherwise). */
+sdrgpu_status sdrgpu_bank_set_demodulator_lanes(sdrgpu_bank *b, int lanes_per_channel);
 /* loop state tap points of one channel: {pll phase, pll frequency, sampling point, detected samples/symbol} */
 sdrgpu_status sdrgpu_bank_get_loop_state(sdrgpu_bank *b, int channel, double *state4);
 /* 4 dibits per byte MSB first (J/dsp/symbol/DibitToByteBufferAssembler.java:58-93); host helper */

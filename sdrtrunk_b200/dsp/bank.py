@@ -143,6 +143,10 @@ class Bank:
         (native.SYNC_P25_PHASE1 / SYNC_P25_PHASE2 / SYNC_NONE).  Symbol bytes become dibit | event << 2 | errors << 5."""
         native.check(native.lib().sdrgpu_bank_set_sync_detector(self._h, int(kind)))
 
+    def setDemodulatorLanes(self, lanes):
+        """tuning / testing: 32, 16 or 1 lanes of a warp per channel in the demodulator kernel, 0 = automatic"""
+        native.check(native.lib().sdrgpu_bank_set_demodulator_lanes(self._h, int(lanes)))
+
     def resetPLL(self, channel):
         native.check(native.lib().sdrgpu_bank_reset_pll(self._h, int(channel)))
 

@@ -268,8 +268,8 @@ def _sync_case(kind, rng, n, offset, with_sync=True):
     return sg.interleave(z + sg.awgn(rng, n, 0.01))
 
 
-@pytest.mark.parametrize("kind", ["c4fm", "lsm", "hdqpsk"])
-def test_sync_detector_and_inversion_feedback_on_device(gpu, kind):
+@pytest.mark.parametrize("kind,lanes", [("c4fm", 0), ("lsm", 0), ("hdqpsk", 0), ("c4fm", 16), ("hdqpsk", 16), ("lsm", 1)])
+def test_sync_detector_and_inversion_feedback_on_device(gpu, kind, lanes):
     """the framer's sync detector + PLLPhaseInversionDetector feedback run inside the demodulator
     kernel.  Channels locked 90 / 180 degrees off (carrier offset = +-rate/4, rate/2) must be corrected at the very
     symbol the reference corrects them: every byte (dibit | event << 2 | errors << 5) equals the oracle's."""
@@ -282,6 +282,7 @@ def test_sync_detector_and_inversion_feedback_on_device(gpu, kind):
     offsets = [0.0, rate / 4 - 50, -rate / 4 - 50, rate / 2 - 100, 120.0, -rate / 4 + 30, rate / 4, 0.0]
     x = np.stack([_sync_case(kind, rng, n, off, with_sync=(k != 7)) for k, off in enumerate(offsets)])
     bank = Bank.preset(preset, len(offsets), 50000.0, taps, max_samples_per_call=8 * 1024)
+    bank.setDemodulatorLanes(lanes)
     bank.setSyncDetector(skind)
     parts = [bank.process(x[:, 2 * a:2 * b]) for a, b in ((0, 8192), (8192, 9000), (9000, 17000), (17000, n))]
     seen = set()
@@ -323,7 +324,8 @@ def _p2_channel(rng, n, offset, holes=()):
     return sg.interleave(z)
 
 
-def test_phase2_framing_on_device(gpu):
+@pytest.mark.parametrize("lanes", [0, 16, 1])
+def test_phase2_framing_on_device(gpu, lanes):
     """SDRGPU_SYNC_P25_PHASE2_FRAMED: the reference's whole Phase 2 framing (P25P2SuperFrameDetector: fragment sync
     state machine, sync-loss accounting, sync detector + PLL inversion feedback while unsynchronized) inside the
     demodulator kernel: every byte (dibit | events << 2) equals the oracle's, through ragged calls, on channels that
@@ -336,6 +338,7 @@ def test_phase2_framing_on_device(gpu):
     x = np.stack([_p2_channel(rng, n, off, holes) for off, holes in cases])
     bank = Bank.preset(preset, len(cases), 50000.0, taps, max_samples_per_call=16 * 1024)
     bank.setSyncDetector(gpu.SYNC_P25_PHASE2_FRAMED)
+    bank.setDemodulatorLanes(lanes)
     cuts = (0, 16384, 17000, 30000, n)
     parts = [bank.process(x[:, 2 * a:2 * b]) for a, b in zip(cuts[:-1], cuts[1:])]
     seen = 0
@@ -359,7 +362,7 @@ def test_phase2_framing_on_device(gpu):
 
 
 def test_phase2_framing_thread_per_channel_kernel(gpu):
-    """the same through psk_wide_kernel (>= 3000 channels)"""
+    """the same through psk_wide_kernel (one thread per channel), 3072 channels"""
     from sdrtrunk_b200.dsp import Bank
     taps = hdqpsk_taps()
     rng = np.random.default_rng(42)
@@ -370,6 +373,7 @@ def test_phase2_framing_thread_per_channel_kernel(gpu):
     x = np.tile(base, (c // len(cases), 1))
     bank = Bank.preset(gpu.PRESET_P25_HDQPSK, c, 50000.0, taps, max_samples_per_call=n)
     bank.setSyncDetector(gpu.SYNC_P25_PHASE2_FRAMED)
+    bank.setDemodulatorLanes(1)
     got = bank.process(x[:, :2 * 9 * 1024])
     got2 = bank.process(x[:, 2 * 9 * 1024:])
     want = []
@@ -383,7 +387,7 @@ def test_phase2_framing_thread_per_channel_kernel(gpu):
 
 
 def test_sync_detector_thread_per_channel_kernel(gpu):
-    """the same through psk_wide_kernel (>= 3000 channels): six distinct channels tiled over 3072"""
+    """the same through psk_wide_kernel (one thread per channel): six distinct channels tiled over 3072"""
     from sdrtrunk_b200.dsp import Bank
     taps = c4fm_taps()
     rng = np.random.default_rng(34)
@@ -393,6 +397,7 @@ def test_sync_detector_thread_per_channel_kernel(gpu):
     c = 3072
     x = np.tile(base, (c // len(offsets), 1))
     bank = Bank.preset(gpu.PRESET_P25_C4FM, c, 50000.0, taps, max_samples_per_call=n)
+    bank.setDemodulatorLanes(1)
     bank.setSyncDetector(gpu.SYNC_P25_PHASE1)
     got = bank.process(x[:, :2 * 6 * 1024])
     got2 = bank.process(x[:, 2 * 6 * 1024:])
@@ -406,24 +411,54 @@ def test_sync_detector_thread_per_channel_kernel(gpu):
         assert np.array_equal(np.concatenate([got[k], got2[k]]), want[k % len(offsets)]), k
 
 
-@pytest.mark.parametrize("c", [1024, 3072])
-def test_many_channels(gpu, c):
+@pytest.mark.parametrize("c,lanes", [(1024, 0), (3072, 0), (4608, 0), (321, 16), (97, 1), (64, 32)])
+def test_many_channels(gpu, c, lanes):
     """BASELINE config 4 shape: >= 1000 channel-domain streams; every channel gets the same input so that one
-    oracle run checks all of them.  1024 channels run one warp per channel (psk_kernel), 3072 one thread per channel
-    (psk_wide_kernel)."""
+    oracle run checks all of them.  By bank size the demodulator runs one warp per channel (1024), two channels per
+    warp (3072) or one thread per channel (4608); the forced layouts use odd channel counts (a last warp with an idle
+    half / idle lanes)."""
     from sdrtrunk_b200.dsp import Bank
     rng = np.random.default_rng(8)
     n = 4 * 1024
     sig, _ = _p25_signal("hdqpsk", rng, n, 0)
     alt, _ = _p25_signal("hdqpsk", rng, n, 1)
     x = np.tile(sig, (c, 1))
-    x[777] = alt
+    odd = min(777, c - 1)
+    x[odd] = alt
     taps = hdqpsk_taps()
-    got = Bank.preset(gpu.PRESET_P25_HDQPSK, c, 50000.0, taps, max_samples_per_call=n).process(x)
+    bank = Bank.preset(gpu.PRESET_P25_HDQPSK, c, 50000.0, taps, max_samples_per_call=n)
+    bank.setDemodulatorLanes(lanes)
+    got = [np.concatenate(parts) for parts in zip(bank.process(x[:, :2 * 3072]), bank.process(x[:, 2 * 3072:]))]
     want = oracle.P25Chain(oracle.HDQPSK, 50000.0, taps).receive(sig)
     want_alt = oracle.P25Chain(oracle.HDQPSK, 50000.0, taps).receive(alt)
     for k in range(c):
-        assert np.array_equal(got[k], want_alt if k == 777 else want), k
+        assert np.array_equal(got[k], want_alt if k == odd else want), k
+
+
+def test_demodulator_layout_can_change_between_calls(gpu):
+    """the three kernel variants share the per-channel state: switching between calls changes nothing"""
+    from sdrtrunk_b200.dsp import Bank
+    rng = np.random.default_rng(18)
+    n = 8 * 1024
+    sigs = [_p25_signal("c4fm", rng, n, k)[0] for k in range(5)]
+    x = np.stack(sigs)
+    taps = c4fm_taps()
+    bank = Bank.preset(gpu.PRESET_P25_C4FM, 5, 50000.0, taps, max_samples_per_call=n)
+    bank.setSyncDetector(gpu.SYNC_P25_PHASE2_FRAMED)      # the framer's state is layout independent as well
+    parts = []
+    for i, lanes in enumerate((32, 16, 1, 16, 32, 1, 0, 16)):
+        bank.setDemodulatorLanes(lanes)
+        parts.append(bank.process(x[:, 2 * 1024 * i:2 * 1024 * (i + 1)]))
+    with pytest.raises(gpu.IllegalArgumentException):
+        bank.setDemodulatorLanes(8)
+    for k in range(5):
+        chain = oracle.P25Chain(oracle.C4FM, 50000.0, taps)
+        chain.attach_sync(oracle.SYNC_P25_PHASE2_FRAMED, 50000.0)
+        assert np.array_equal(np.concatenate([p[k] for p in parts]), chain.receive(sigs[k])), k
+    # the sync detectors keep layout-specific state: the layout has to be chosen before they are enabled
+    bank.setSyncDetector(gpu.SYNC_P25_PHASE1)
+    with pytest.raises(gpu.IllegalStateException):
+        bank.setDemodulatorLanes(1)
 
 
 # ------------------------------------------------------------------------------------------------ pipeline
