@@ -18,7 +18,10 @@
 // The Hilbert transform is a plain FIR once the Java's circular buffer + index map are unrolled (checked against
 // the literal restatement in oracle/orc_airspy.c): with n the second sample of pair k,
 //     I[k] = s * f[n - 24],   Q[k] = s * sum_{x = 0, 2, .., 22} h[x] * (f[n - 47 + x] - f[n - x - 1]),   s = (-1)^k
-// accumulated in x order with separately rounded products (no FMA), h[x] = 2 * -|halfband47[x]|.
+// accumulated in x order with separately rounded products (no FMA), h[x] = 2 * -|halfband47[x]|.  Q only touches the
+// first sample of each pair, I only the second, so the DC stage writes the filtered stream as two planes (even- and
+// odd-indexed samples): e[k] = f[2k], o[k] = f[2k+1], and  I[k] = s * o[k - 12],
+// Q[k] = s * sum_j h[2j] * (e[k - 23 + j] - e[k - j]) -- every load of the Hilbert kernel is contiguous across lanes.
 #include <cmath>
 #include <cstdint>
 
@@ -31,7 +34,7 @@ namespace {
 constexpr int kSegment = 2048;   // samples per thread of the DC stage (more, shorter segments: more warps to hide latency)
 constexpr int kWarmup = 4096;    // samples a thread runs ahead of its segment from the guessed state
 constexpr int kRepairRounds = 2; // parallel repairs of late-merging segments before the sequential fallback
-constexpr int kHistory = 47;     // HilbertTransform: the filter length; ages 1 .. 47 behind the newest sample
+constexpr int kPlaneHistory = 24; // HilbertTransform looks 47 samples back = 24 even-indexed and 12 odd-indexed ones
 constexpr float kRatio = 0.01f;  // AirspySampleConverter.java:31
 
 // Filters.HALF_BAND_FILTER_47T (J/dsp/filter/Filters.java:1708-1722), even taps left of the centre, turned into
@@ -125,9 +128,15 @@ __device__ __forceinline__ float dc_step(float &average, float x)
     return filtered;
 }
 
-// One thread per segment.  filtered: this call's samples (the caller placed kHistory older ones in front of it).
+// filtered sample i of the call goes to the even plane (i even) or the odd plane, position i / 2
+struct Planes {
+    float *even, *odd;   // this call's first entries; kPlaneHistory older ones sit in front of each
+};
+__device__ __forceinline__ void store_filtered(const Planes &pl, int i, float v) { ((i & 1) ? pl.odd : pl.even)[i >> 1] = v; }
+
+// One thread per segment.
 __global__ void __launch_bounds__(32) airspy_dc_kernel(const uint8_t *__restrict__ raw, int n, int packed, int aligned,
-                                                         const AirspyState *__restrict__ state, float *__restrict__ filtered,
+                                                         const AirspyState *__restrict__ state, Planes filtered,
                                                          float *__restrict__ seg_start, float *__restrict__ seg_end)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -156,13 +165,18 @@ __global__ void __launch_bounds__(32) airspy_dc_kernel(const uint8_t *__restrict
                 for (int j = 0; j < 32; j++) dc_step(average, x[j]);
             } else {
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    float4 f;
-                    f.x = dc_step(average, x[j]);
-                    f.y = dc_step(average, x[j + 1]);
-                    f.z = dc_step(average, x[j + 2]);
-                    f.w = dc_step(average, x[j + 3]);
-                    *reinterpret_cast<float4 *>(filtered + i + j) = f;
+                for (int j = 0; j < 32; j += 8) {   // eight samples = four of each plane (i is a multiple of 32)
+                    float4 fe, fo;
+                    fe.x = dc_step(average, x[j]);
+                    fo.x = dc_step(average, x[j + 1]);
+                    fe.y = dc_step(average, x[j + 2]);
+                    fo.y = dc_step(average, x[j + 3]);
+                    fe.z = dc_step(average, x[j + 4]);
+                    fo.z = dc_step(average, x[j + 5]);
+                    fe.w = dc_step(average, x[j + 6]);
+                    fo.w = dc_step(average, x[j + 7]);
+                    *reinterpret_cast<float4 *>(filtered.even + ((i + j) >> 1)) = fe;
+                    *reinterpret_cast<float4 *>(filtered.odd + ((i + j) >> 1)) = fo;
                 }
             }
         }
@@ -171,7 +185,7 @@ __global__ void __launch_bounds__(32) airspy_dc_kernel(const uint8_t *__restrict
     for (; i < end; i++) {
         if (i == (int)begin) seg_start[k] = average;
         const float v = dc_step(average, raw_sample(raw, (size_t)i, pk));
-        if (i >= (int)begin) filtered[i] = v;
+        if (i >= (int)begin) store_filtered(filtered, i, v);
     }
     seg_end[k] = average;
 }
@@ -183,7 +197,7 @@ __global__ void __launch_bounds__(32) airspy_dc_kernel(const uint8_t *__restrict
 // seg_end[k - 1] a thread sees, it records the one it used in seg_start[k], and the check below accepts the result
 // only if every start equals its predecessor's end once all rounds are over.
 __global__ void __launch_bounds__(32) airspy_repair_kernel(const uint8_t *__restrict__ raw, int n, int packed, int n_segments,
-                                                             float *__restrict__ filtered, float *__restrict__ seg_start,
+                                                             Planes filtered, float *__restrict__ seg_start,
                                                              float *__restrict__ seg_end, int *__restrict__ repaired)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x + 1;
@@ -193,7 +207,7 @@ __global__ void __launch_bounds__(32) airspy_repair_kernel(const uint8_t *__rest
     if (__float_as_uint(seg_start[k]) == __float_as_uint(truth)) return;
     const int begin = k * kSegment, end = min(n, begin + kSegment);
     float average = truth;
-    for (int i = begin; i < end; i++) filtered[i] = dc_step(average, raw_sample(raw, (size_t)i, packed != 0));
+    for (int i = begin; i < end; i++) store_filtered(filtered, i, dc_step(average, raw_sample(raw, (size_t)i, packed != 0)));
     seg_start[k] = truth;
     seg_end[k] = average;
     atomicAdd(repaired, 1);
@@ -211,7 +225,7 @@ __global__ void airspy_check_kernel(int n_segments, const float *__restrict__ se
 
 // commits the new average; after a mismatch (not seen in practice) redoes the stream sequentially from the carried state
 __global__ void airspy_commit_kernel(const uint8_t *__restrict__ raw, int n, int packed, int n_segments,
-                                     const float *__restrict__ seg_end, AirspyState *state, float *__restrict__ filtered,
+                                     const float *__restrict__ seg_end, AirspyState *state, Planes filtered,
                                      int *__restrict__ total_mismatches)
 {
     if (state->mismatches == 0) {
@@ -219,59 +233,70 @@ __global__ void airspy_commit_kernel(const uint8_t *__restrict__ raw, int n, int
         return;
     }
     float average = state->average;
-    for (int i = 0; i < n; i++) filtered[i] = dc_step(average, raw_sample(raw, (size_t)i, packed != 0));
+    for (int i = 0; i < n; i++) store_filtered(filtered, i, dc_step(average, raw_sample(raw, (size_t)i, packed != 0)));
     state->average = average;
     atomicAdd(total_mismatches, state->mismatches);
     state->mismatches = 0;
 }
 
-// Four complex outputs per thread: the 56 filtered samples f[8t - 48 .. 8t + 7] they need come in through fourteen
-// 16-byte loads (f is 16-byte aligned and has kHistory + 1 older samples in front of it).
-__global__ void airspy_hilbert_kernel(const float *__restrict__ f, int n_pairs, const AirspyState *__restrict__ state,
-                                      float2 *__restrict__ out)
+// Four complex outputs per thread, k0 = 4 t: e[k0 - 24 .. k0 + 3] in seven 16-byte loads, o[k0 - 12 .. k0 - 9] in one;
+// consecutive threads read consecutive 16 bytes.  Both planes are 16-byte aligned at entry 0.
+__global__ void airspy_hilbert_kernel(Planes f, int n_pairs, const AirspyState *__restrict__ state, float2 *__restrict__ out,
+                                      int out_aligned)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int k0 = 4 * t;
     if (k0 >= n_pairs) return;
-    float w[56];   // w[j] = f[8 t - 48 + j]
-    const float4 *src = reinterpret_cast<const float4 *>(f + 8 * (long long)t - 48);
-    const int have = min(4, n_pairs - k0);   // the call's last thread may own fewer than four pairs: do not read past them
+    float w[28];   // w[j] = e[k0 - 24 + j]
+    const float4 *src = reinterpret_cast<const float4 *>(f.even + k0 - 24);
 #pragma unroll
-    for (int q = 0; q < 14; q++) {
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (q < 12 || 2 * have > 4 * (q - 12)) v = __ldg(src + q);
+    for (int q = 0; q < 7; q++) {
+        const float4 v = __ldg(src + q);   // the last load may run up to 3 entries past the call: inside the padding
         w[4 * q] = v.x;
         w[4 * q + 1] = v.y;
         w[4 * q + 2] = v.z;
         w[4 * q + 3] = v.w;
     }
+    const float4 centre4 = __ldg(reinterpret_cast<const float4 *>(f.odd + k0 - 12));
+    const float centre[4] = {centre4.x, centre4.y, centre4.z, centre4.w};
     const int inverted = state->inverted;
+    const int have = min(4, n_pairs - k0);
+    float2 r[4];
 #pragma unroll
     for (int p = 0; p < 4; p++) {
-        if (p < have) {
-            const int newest = 48 + 2 * p + 1;   // index in w of the second sample of pair k0 + p
-            float acc = 0.0f;
+        float acc = 0.0f;
 #pragma unroll
-            for (int j = 0; j < 12; j++) {
-                const int x = 2 * j;
-                acc = __fadd_rn(acc, __fmul_rn(c_hilbert[j], __fsub_rn(w[newest - (kHistory - x)], w[newest - (x + 1)])));
-            }
-            const float centre = w[newest - 24];
-            const bool invert = ((inverted + k0 + p) & 1) != 0;
-            out[k0 + p] = invert ? make_float2(-centre, -acc) : make_float2(centre, acc);
-        }
+        for (int j = 0; j < 12; j++) acc = __fadd_rn(acc, __fmul_rn(c_hilbert[j], __fsub_rn(w[p + 1 + j], w[p + 24 - j])));
+        const bool invert = ((inverted + k0 + p) & 1) != 0;
+        r[p] = invert ? make_float2(-centre[p], -acc) : make_float2(centre[p], acc);
+    }
+    if (have == 4 && out_aligned) {
+        reinterpret_cast<float4 *>(out + k0)[0] = make_float4(r[0].x, r[0].y, r[1].x, r[1].y);
+        reinterpret_cast<float4 *>(out + k0)[1] = make_float4(r[2].x, r[2].y, r[3].x, r[3].y);
+    } else {
+#pragma unroll
+        for (int p = 0; p < 4; p++)
+            if (p < have) out[k0 + p] = r[p];
     }
 }
 
-// the last kHistory filtered samples of [history | this call] become the next call's history; flips the invert flag
-__global__ void airspy_carry_kernel(float *__restrict__ with_history, int n, AirspyState *state)
+// the last kPlaneHistory entries of [history | this call] of each plane become the next call's history; flips the
+// invert flag.  plane pointers here are the allocation starts (history first).
+__global__ void airspy_carry_kernel(float *__restrict__ even_with_history, float *__restrict__ odd_with_history, int n_pairs,
+                                    AirspyState *state)
 {
-    __shared__ float keep[kHistory];
+    __shared__ float keep[2][kPlaneHistory];
     const int t = threadIdx.x;
-    if (t < kHistory) keep[t] = with_history[n + t];
+    if (t < kPlaneHistory) {
+        keep[0][t] = even_with_history[n_pairs + t];
+        keep[1][t] = odd_with_history[n_pairs + t];
+    }
     __syncthreads();
-    if (t < kHistory) with_history[t] = keep[t];
-    if (t == 0) state->inverted = (state->inverted + n / 2) & 1;
+    if (t < kPlaneHistory) {
+        even_with_history[t] = keep[0][t];
+        odd_with_history[t] = keep[1][t];
+    }
+    if (t == 0) state->inverted = (state->inverted + n_pairs) & 1;
 }
 
 }  // namespace
@@ -283,7 +308,7 @@ struct sdrgpu_airspy {
     int packed = 0;
     cudaStream_t stream = nullptr;   // own stream of the stand-alone converter
     AirspyState *d_state = nullptr;
-    float *d_filtered = nullptr;     // [1 pad | kHistory older samples | max_samples | 8 pad]
+    float *d_even = nullptr, *d_odd = nullptr;   // filtered planes: [kPlaneHistory older | max_samples / 2 | 8 pad] each
     float *d_seg_start = nullptr, *d_seg_end = nullptr;
     int *d_total_mismatches = nullptr, *d_repaired = nullptr;
     uint8_t *d_raw = nullptr;        // staging for host input
@@ -316,9 +341,12 @@ sdrgpu_status airspy_create(sdrgpu_airspy **out, int max_samples)
     }
     CHK(cudaMalloc(&a->d_state, sizeof(AirspyState)));
     CHK(cudaMemset(a->d_state, 0, sizeof(AirspyState)));
-    // + 1 in front (alignment of the 16-byte stores), + 8 behind (the Hilbert kernel's last 16-byte load)
-    CHK(cudaMalloc(&a->d_filtered, sizeof(float) * ((size_t)max_samples + kHistory + 1 + 8)));
-    CHK(cudaMemset(a->d_filtered, 0, sizeof(float) * ((size_t)max_samples + kHistory + 1 + 8)));
+    // + 8 behind: the Hilbert kernel's last 16-byte load
+    const size_t plane = sizeof(float) * ((size_t)max_samples / 2 + kPlaneHistory + 8);
+    CHK(cudaMalloc(&a->d_even, plane));
+    CHK(cudaMemset(a->d_even, 0, plane));
+    CHK(cudaMalloc(&a->d_odd, plane));
+    CHK(cudaMemset(a->d_odd, 0, plane));
     CHK(cudaMalloc(&a->d_seg_start, sizeof(float) * (size_t)segments));
     CHK(cudaMalloc(&a->d_seg_end, sizeof(float) * (size_t)segments));
     CHK(cudaMalloc(&a->d_total_mismatches, sizeof(int)));
@@ -334,7 +362,8 @@ void airspy_destroy(sdrgpu_airspy *a)
 {
     if (!a) return;
     cudaFree(a->d_state);
-    cudaFree(a->d_filtered);
+    cudaFree(a->d_even);
+    cudaFree(a->d_odd);
     cudaFree(a->d_seg_start);
     cudaFree(a->d_seg_end);
     cudaFree(a->d_total_mismatches);
@@ -353,7 +382,7 @@ sdrgpu_status airspy_enqueue(sdrgpu_airspy *a, const uint8_t *d_raw, int n_sampl
     if (n_samples == 0) return SDRGPU_OK;
     if (n_samples > a->max_samples) return fail(SDRGPU_ERR_OVERFLOW, "%d samples exceed the converter's capacity %d", n_samples, a->max_samples);
     const int segments = (n_samples + kSegment - 1) / kSegment;
-    float *f = a->d_filtered + kHistory + 1;   // + 1: float4 stores of the DC stage need 16-byte alignment
+    const Planes f{a->d_even + kPlaneHistory, a->d_odd + kPlaneHistory};   // 96 bytes in: 16-byte aligned
     const int aligned = ((uintptr_t)d_raw & 15) == 0;
     airspy_dc_kernel<<<(segments + 31) / 32, 32, 0, stream>>>(d_raw, n_samples, packed, aligned, a->d_state, f, a->d_seg_start, a->d_seg_end);
     if (segments > 1) {
@@ -364,8 +393,9 @@ sdrgpu_status airspy_enqueue(sdrgpu_airspy *a, const uint8_t *d_raw, int n_sampl
     }
     airspy_commit_kernel<<<1, 1, 0, stream>>>(d_raw, n_samples, packed, segments, a->d_seg_end, a->d_state, f, a->d_total_mismatches);
     const int pairs = n_samples / 2;
-    airspy_hilbert_kernel<<<((pairs + 3) / 4 + 127) / 128, 128, 0, stream>>>(f, pairs, a->d_state, d_out);
-    airspy_carry_kernel<<<1, 64, 0, stream>>>(a->d_filtered + 1, n_samples, a->d_state);
+    airspy_hilbert_kernel<<<((pairs + 3) / 4 + 127) / 128, 128, 0, stream>>>(f, pairs, a->d_state, d_out,
+                                                                             ((uintptr_t)d_out & 15) == 0);
+    airspy_carry_kernel<<<1, 64, 0, stream>>>(a->d_even, a->d_odd, pairs, a->d_state);
     count_launch(segments > 1 ? 5 + kRepairRounds : 4);
     SDRGPU_CUDA(cudaGetLastError());
     return SDRGPU_OK;
@@ -374,7 +404,8 @@ sdrgpu_status airspy_enqueue(sdrgpu_airspy *a, const uint8_t *d_raw, int n_sampl
 sdrgpu_status airspy_reset(sdrgpu_airspy *a, cudaStream_t stream)
 {
     SDRGPU_CUDA(cudaMemsetAsync(a->d_state, 0, sizeof(AirspyState), stream));
-    SDRGPU_CUDA(cudaMemsetAsync(a->d_filtered, 0, sizeof(float) * (kHistory + 1), stream));
+    SDRGPU_CUDA(cudaMemsetAsync(a->d_even, 0, sizeof(float) * kPlaneHistory, stream));
+    SDRGPU_CUDA(cudaMemsetAsync(a->d_odd, 0, sizeof(float) * kPlaneHistory, stream));
     return SDRGPU_OK;
 }
 
