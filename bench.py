@@ -477,7 +477,7 @@ class GpuWorkload:
                                     max_samples_per_call=self.n_blocks, device=local_rank)
             self.bank.setStream(self.stream.cuda_stream)
             self.pipeline = Pipeline(self.chan, self.bank)
-            self.chunks = int(os.environ.get("SDRGPU_BENCH_CHUNKS", "4"))
+            self.chunks = int(os.environ.get("SDRGPU_BENCH_CHUNKS", "8"))
             self.pipeline.setChunks(self.chunks)
             self.sym_stride = self.n_blocks // 8 + 64          # > 4800/50000 symbols per sample
             self.sym_dev = torch.zeros((m, self.sym_stride), dtype=torch.uint8, device=dev)

@@ -308,7 +308,7 @@ sdrgpu_status sdrgpu_bank_last_kernel_ms(sdrgpu_bank *b, float *ms2);
 typedef struct sdrgpu_pipeline sdrgpu_pipeline;
 sdrgpu_status sdrgpu_pipeline_create(sdrgpu_pipeline **p, sdrgpu_channelizer *chan, sdrgpu_bank *bank);
 sdrgpu_status sdrgpu_pipeline_destroy(sdrgpu_pipeline *p); /* does not destroy chan / bank; call it before theirs */
-/* a process call is cut into `chunks` time chunks (default 4, behind a ramp of smaller leading chunks; 1 = single pass) so that copies, channelizer / filter
+/* a process call is cut into `chunks` time chunks (default 8, behind a ramp of smaller leading chunks; 1 = single pass) so that copies, channelizer / filter
  * kernels and the latency-bound demodulator of successive chunks overlap; the results do not depend on it */
 sdrgpu_status sdrgpu_pipeline_set_chunks(sdrgpu_pipeline *p, int chunks);
 sdrgpu_status sdrgpu_pipeline_process(sdrgpu_pipeline *p, const void *iq, int n_floats, int in_mem,
