@@ -1,0 +1,46 @@
+#!/usr/bin/env python3
+"""Demodulator kernel time by bank size and lanes per channel (C4FM, decision directed): the data behind the
+automatic layout choice in bank.cu.  usage (GPU box): python tools/psk_layout_sweep.py"""
+import os
+import sys
+
+import numpy as np
+import scipy.signal as ss
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import siggen as sg  # noqa: E402
+from sdrtrunk_b200 import native  # noqa: E402
+from sdrtrunk_b200.dsp import Bank  # noqa: E402
+
+
+def main():
+    native.init(0)
+    rng = np.random.default_rng(0)
+    n = 24 * 1024
+    fir = ss.remez(72, [0, 5100, 6500, 25000], [1, 0], fs=50000).astype(np.float32)
+    base = []
+    for k in range(8):
+        dib = rng.integers(0, 4, int(n * 4800 / 50000) + 8)
+        z = sg.c4fm(dib, carrier_offset=rng.uniform(-200, 200), timing_phase=rng.uniform(0, 1), n_samples=n)
+        base.append(sg.interleave(z + sg.awgn(rng, n, 0.03)))
+    base = np.stack(base)
+    for c in (400, 800, 1200, 1600, 2048, 3072, 4096, 6144):
+        x = np.tile(base, (c // 8, 1))
+        row = []
+        for lanes in (32, 16, 1):
+            bank = Bank.preset(native.PRESET_P25_C4FM, c, 50000.0, fir, max_samples_per_call=n)
+            bank.setDemodulatorLanes(lanes)
+            bank.enableTiming(True)
+            best = 1e9
+            for _ in range(3):
+                bank.process(x)
+                best = min(best, bank.lastKernelMs()[1])
+            row.append(best)
+            bank.dispose()
+        print("%5d channels: 32 lanes %.3f ms, 16 lanes %.3f ms, 1 lane %.3f ms" % (c, *row), flush=True)
+
+
+if __name__ == "__main__":
+    main()
