@@ -440,3 +440,35 @@ def test_phase2_super_frame_detector():
     assert not sync[:279].any() and sync[279:2999].all() and not sync[3500:4400].all()
     assert np.any(events & oracle.P2_EVENT_SYNC_LOSS)
     assert np.any((events >> 3) & 3)                            # a rotated sync pattern was seen while unsynchronized
+
+
+def test_airspy_oracle_against_closed_form_fir():
+    """The oracle restates HilbertTransform literally (48-slot circular buffer, index map with its wrap-around special
+    case).  Unrolled, that is a 47-tap FIR on the DC-filtered stream -- the form the CUDA kernels use:
+    I[k] = s f[n - 24], Q[k] = s sum_x h[x] (f[n - 47 + x] - f[n - x - 1]), n = 2k + 1, s = (-1)^k.  Both must agree
+    bit for bit, DC recursion included."""
+    f32 = np.float32
+    rng = np.random.default_rng(3)
+    n = 3000
+    raw12 = rng.integers(0, 4096, n).astype(np.uint16)
+    want = oracle.AirspySampleConverter().convert(raw12.astype("<u2").view(np.uint8))
+    x = ((raw12.astype(np.int32) & 0xFFF) - 2048).astype(np.float32) * f32(1 / 2048)
+    f = np.zeros(n + 47, np.float32)
+    a, r = f32(0), f32(0.01)
+    for i in range(n):
+        d = f32(x[i] - a)
+        a = f32(a + f32(r * d))
+        f[47 + i] = d
+    half_band = [-0.000998606272947510, 0.001695637278417295, -0.003054430179754289, 0.005055504379767936,
+                 -0.007901319195893647, 0.011873357051047719, -0.017411159379930066, 0.025304817427568772,
+                 -0.037225225204559217, 0.057533286997004301, -0.102327462004259350, 0.317034472508947400]
+    h = [f32(2.0) * -abs(f32(v)) for v in half_band]
+    out = np.zeros(n, np.float32)
+    for k in range(n // 2):
+        newest = 47 + 2 * k + 1
+        acc = f32(0)
+        for j in range(12):
+            acc = f32(acc + f32(h[j] * f32(f[newest - (47 - 2 * j)] - f[newest - (2 * j + 1)])))
+        sign = -1 if k & 1 else 1
+        out[2 * k], out[2 * k + 1] = sign * f[newest - 24], sign * acc
+    assert np.array_equal(out, want)
