@@ -110,6 +110,25 @@ def test_custom_taps_per_channel_generic_path(gpu):
     assert sg.rel_rms(got, want) < TOL
 
 
+@pytest.mark.parametrize("seed", range(8))
+def test_random_channel_counts_and_taps_per_channel(gpu, seed):
+    """generic kernel: channel counts with every kind of factorisation (powers of two, 3s, 5s, large primes), taps per
+    channel other than the reference's 9, random prototypes, ragged buffers"""
+    from sdrtrunk_b200.dsp import ComplexPolyphaseChannelizerM2
+    rng = np.random.default_rng(1000 + seed)
+    m = int(rng.choice([4, 6, 14, 22, 34, 46, 62, 74, 128, 134, 250, 256, 358, 486, 514, 1000]))
+    t = int(rng.choice([1, 2, 3, 5, 9, 12]))
+    taps = (rng.standard_normal(m * t) / (m * t)).astype(np.float32)
+    n = (10 + int(rng.integers(0, 40))) * (m // 2) + int(rng.integers(0, m // 2))
+    x = sg.interleave(rng.standard_normal(n) + 1j * rng.standard_normal(n))
+    want = oracle.Channelizer(taps, m).receive(x, mode="f64")
+    ch = ComplexPolyphaseChannelizerM2(taps, 25000 * m, m)
+    cut = 2 * int(rng.integers(0, n))
+    got = np.concatenate([ch.receive(x[:cut]), ch.receive(x[cut:])])
+    assert got.shape == want.shape, (m, t)
+    assert sg.rel_rms(got, want) < TOL, (m, t)
+
+
 def test_errors_mirror_reference(gpu):
     from sdrtrunk_b200 import native
     from sdrtrunk_b200.dsp import ComplexPolyphaseChannelizerM2
