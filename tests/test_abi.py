@@ -65,3 +65,18 @@ def test_pack_dibits_host_helper():
     assert n == 10
     assert np.array_equal(out[:n], oracle.pack_dibits(d))
     assert out[0] == (d[0] << 6 | d[1] << 4 | d[2] << 2 | d[3])
+
+
+def test_header_is_plain_c():
+    """the drop-in boundary is a C ABI: include/sdrgpu.h must compile as C99 (what jextract / cgo / ctypesgen read) and
+    as C++, with no torch / CUDA types in it"""
+    import shutil
+    import subprocess
+    header = os.path.join(ROOT, "include", "sdrgpu.h")
+    text = re.sub(r"/\*.*?\*/", "", open(header).read(), flags=re.S)      # declarations only, comments stripped
+    assert "torch" not in text and "cudaStream_t" not in text and "#include <cuda" not in text
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no C compiler")
+    subprocess.check_call([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", header])
+    subprocess.check_call([gcc, "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", "-x", "c++", header])
