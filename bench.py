@@ -350,7 +350,7 @@ def synth_dqpsk_channels(torch, dev, n_channels, n, seed, symbol_rate=6000.0, fs
 
 def run_config4(args, rank, world, local_rank):
     """BASELINE configs[3]: P25 Phase 2 HDQPSK on >= 1000 channel-domain streams (no channelizer): 154-tap FIR -> AGC ->
-    Gardner timing recovery, one warp per channel.  Channels are sharded over the ranks (level 3 of SURVEY 8e)."""
+    Gardner timing recovery (demodulator layout chosen by the bank size).  Channels are sharded over the ranks (level 3 of SURVEY 8e)."""
     import scipy.signal as ss
     import torch
     import torch.distributed as dist
@@ -422,7 +422,7 @@ def run_config4(args, rank, world, local_rank):
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": "configs[3]: P25 Phase 2 HDQPSK, %d channel-domain streams per GPU at 50 kHz "
                                        "(channel samples, not tuner samples): 154-tap FIR + AGC + Gardner DQPSK "
-                                       "timing recovery, one warp per channel" % channels,
+                                       "timing recovery" % channels,
                            "channels_per_gpu": channels, "samples_per_channel_per_step": n,
                            "sharding": "channel rows per GPU, no collective"},
                 "realtime_channels": channels * world * (n / 50000.0) / (ms_step * 1e-3),
@@ -431,7 +431,7 @@ def run_config4(args, rank, world, local_rank):
                 "roofline": {"bound": "hbm", "achieved": alg / (k_demod * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                              "frac": alg / (k_demod * 1e-3) / 1e9 / peak, "traffic": None, "kernel": "psk_kernel<gardner>",
                              "kernel_ms": k_demod, "algorithmic_bytes_per_launch": alg, "peak_source": peak_src,
-                             "note": "latency bound: one warp per channel"}}
+                             "note": "latency bound per-symbol feedback loop; lanes per channel chosen by the bank size"}}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
