@@ -67,6 +67,8 @@ def lib():
         "orc_convert_s16le": (None, [C.c_void_p, C.c_int, _f32p]),
         "orc_get_channel": (None, [_f32p, C.c_int, C.c_int, C.c_int, _f32p]),
         "orc_apply_gain": (None, [_f32p, C.c_int, C.c_double]),
+        "orc_osc_init": (None, [vp, C.c_double, C.c_double]),
+        "orc_osc_mix": (None, [vp, _f32p, C.c_int]),
         "orc_one_channel_create": (vp, [C.c_double, C.c_int, C.c_double]),
         "orc_one_channel_destroy": (None, [vp]),
         "orc_one_channel_set_frequency_offset": (None, [vp, C.c_longlong]),
@@ -420,6 +422,29 @@ class SquelchingFMDemodulator:
         out = np.zeros(a.size // 2, np.float32)
         lib().orc_sqfm_demodulate_buffer(C.byref(self.s), p, a.size, out.ctypes.data_as(_f32p))
         return out
+
+
+class _Osc(C.Structure):
+    _fields_ = [("angle_i", C.c_float), ("angle_q", C.c_float), ("cur_i", C.c_float), ("cur_q", C.c_float)]
+
+
+class Oscillator:
+    """J/dsp/mixer/Oscillator.java: mixComplex(samples) = sample * current, then rotate() + fastNormalize."""
+
+    def __init__(self, frequency, sample_rate):
+        self.o = _Osc()
+        lib().orc_osc_init(C.byref(self.o), float(frequency), float(sample_rate))
+
+    def mix(self, iq):
+        a = np.array(iq, np.float32, copy=True)
+        lib().orc_osc_mix(C.byref(self.o), a.ctypes.data_as(_f32p), a.size)
+        return a
+
+
+def apply_gain(iq, gain):
+    a = np.array(iq, np.float32, copy=True)
+    lib().orc_apply_gain(a.ctypes.data_as(_f32p), a.size, float(gain))
+    return a
 
 
 def agc_block(iq):

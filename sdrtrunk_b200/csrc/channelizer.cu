@@ -642,6 +642,87 @@ __global__ void __launch_bounds__(32) post_channel_kernel(float *out, long long 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// One-bin channels with a frequency offset (the usual case: a requested channel frequency is rarely the centre of its
+// polyphase bin).  The oscillator is a float recursion -- rotate by the angle, fastNormalize -- that is neutrally stable
+// in phase: two runs never merge, so unlike the Airspy DC filter it cannot be cut into speculative segments, and one
+// chain step costs 44 cycles (12 fma-pipe instructions): 1.1 ms per 50 000-sample row, 14 x the whole polyphase
+// kernel.  But the values do not depend on the samples.  osc_produce_kernel therefore runs AHEAD: after every call it
+// tops a per-channel ring up to one call's worth of oscillator values on a side stream, one thread per channel, while
+// the caller's FIR / demodulator kernels run; the call itself only does the element-wise osc_mix_kernel.
+// (AbstractOscillator.mixComplex, J/dsp/mixer/AbstractOscillator.java:102-116: sample * current, then rotate();
+// Oscillator.rotate + Complex.fastNormalize, J/dsp/mixer/Oscillator.java:42-68.)
+// ---------------------------------------------------------------------------------------------------------------
+struct MixChannel {
+    int row;
+    float angle_i, angle_q;
+    double gain;
+};
+
+__global__ void __launch_bounds__(32) osc_produce_kernel(const MixChannel *__restrict__ chans, float2 *__restrict__ state,
+                                                           float2 *__restrict__ ring, int ring_len, long long start, int count,
+                                                           int n_mix)
+{
+    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= n_mix) return;
+    const float angle_i = chans[ch].angle_i, angle_q = chans[ch].angle_q;
+    float cur_i = state[ch].x, cur_q = state[ch].y;
+    float2 *r = ring + (size_t)ch * ring_len;
+    int pos = (int)(start % ring_len);
+#define SDRGPU_OSC_ROTATE()                                                                        \
+    {                                                                                              \
+        const float ni = __fsub_rn(__fmul_rn(cur_i, angle_i), __fmul_rn(cur_q, angle_q));          \
+        const float nq = __fadd_rn(__fmul_rn(cur_q, angle_i), __fmul_rn(cur_i, angle_q));          \
+        const float scalor = __fsub_rn(1.9999f, __fadd_rn(__fmul_rn(ni, ni), __fmul_rn(nq, nq)));  \
+        cur_i = __fmul_rn(ni, scalor);                                                             \
+        cur_q = __fmul_rn(nq, scalor);                                                             \
+    }
+    int k = 0;
+    while (k < count) {
+        if ((pos & 1) == 0 && k + 8 <= count && pos + 8 <= ring_len) {
+            // eight steps with nothing but the recursion between them, then four 16-byte stores (ring_len is even and
+            // the rows are 16-byte aligned)
+            float4 w[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                w[j].x = cur_i;
+                w[j].y = cur_q;
+                SDRGPU_OSC_ROTATE()
+                w[j].z = cur_i;
+                w[j].w = cur_q;
+                SDRGPU_OSC_ROTATE()
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++) reinterpret_cast<float4 *>(r + pos)[j] = w[j];
+            pos += 8;
+            k += 8;
+        } else {
+            r[pos] = make_float2(cur_i, cur_q);
+            SDRGPU_OSC_ROTATE()
+            pos += 1;
+            k += 1;
+        }
+        if (pos >= ring_len) pos = 0;
+    }
+#undef SDRGPU_OSC_ROTATE
+    state[ch] = make_float2(cur_i, cur_q);
+}
+
+// grid (ceil(n / 256), n_mix): row[k] = (float)((double)(row[k] * osc[start + k]) * gain)
+__global__ void osc_mix_kernel(float *out, long long out_stride, const MixChannel *__restrict__ chans,
+                               const float2 *__restrict__ ring, int ring_len, long long start, int n)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const MixChannel c = chans[blockIdx.y];
+    float2 *row = reinterpret_cast<float2 *>(out + (size_t)c.row * out_stride);
+    const float2 v = row[k];
+    const float2 z = ring[(size_t)blockIdx.y * ring_len + (int)((start + k) % ring_len)];
+    const float mi = __fsub_rn(__fmul_rn(v.x, z.x), __fmul_rn(v.y, z.y));
+    const float mq = __fadd_rn(__fmul_rn(v.y, z.x), __fmul_rn(v.x, z.y));
+    row[k] = make_float2(__double2float_rn(__dmul_rn((double)mi, c.gain)), __double2float_rn(__dmul_rn((double)mq, c.gain)));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // tuner sample converters (ByteSampleConverter / SignedByteSampleConverter lookup tables, ConversionUtils 16-bit)
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float convert_value(int format, const void *src, size_t i)
@@ -713,6 +794,15 @@ struct sdrgpu_channelizer {
     PostChannel *d_post = nullptr;
     PostState *d_post_state = nullptr;
     float *d_out2 = nullptr;           // scratch rows [n_rows - n_sel][2 * max_blocks]
+    // one-bin frequency-corrected channels: oscillator values produced ahead of use (osc_produce_kernel)
+    int n_mix = 0, osc_ring_len = 0;
+    MixChannel *d_mix = nullptr;
+    float2 *d_mix_state = nullptr;     // oscillator vector at the producer's position
+    float2 *d_osc = nullptr;           // [n_mix][osc_ring_len]
+    long long osc_produced = 0, osc_consumed = 0, osc_safe = 0;   // osc_safe: produced by launches already waited for
+    cudaStream_t osc_stream = nullptr;
+    cudaEvent_t ev_mix = nullptr, ev_osc = nullptr;
+    bool osc_pending = false;
     SynthFilter synth{};
     int gain_exact = 1;
     int identity = 0;
@@ -733,6 +823,7 @@ sdrgpu_status upload_selection(sdrgpu_channelizer *h)
     std::vector<float> gf;
     std::vector<double> gd;
     std::vector<PostChannel> post;
+    std::vector<MixChannel> mix;
     int exact = 1, n_two = 0;
     for (int i = 0; i < n; i++) {
         const sdrgpu_output_channel &c = h->channels[i];
@@ -754,7 +845,8 @@ sdrgpu_status upload_selection(sdrgpu_channelizer *h)
             pc.angle_i = (float)cos((double)angle);
             pc.angle_q = (float)sin((double)angle);
             pc.gain = c.gain;
-            post.push_back(pc);
+            if (c.bin2 >= 0) post.push_back(pc);                                        // two-bin: post_channel_kernel
+            else mix.push_back(MixChannel{pc.row, pc.angle_i, pc.angle_q, pc.gain});    // one bin + offset: look-ahead
         }
     }
     for (int i = 0; i < n; i++)
@@ -770,6 +862,15 @@ sdrgpu_status upload_selection(sdrgpu_channelizer *h)
     cudaFree(h->d_post);
     cudaFree(h->d_post_state);
     cudaFree(h->d_out2);
+    if (h->osc_stream) SDRGPU_CUDA(cudaStreamSynchronize(h->osc_stream));
+    cudaFree(h->d_mix);
+    cudaFree(h->d_mix_state);
+    cudaFree(h->d_osc);
+    h->d_mix = nullptr;
+    h->d_mix_state = nullptr;
+    h->d_osc = nullptr;
+    h->osc_produced = h->osc_consumed = h->osc_safe = 0;
+    h->osc_pending = false;
     h->d_sel = nullptr;
     h->d_gain_f = nullptr;
     h->d_gain_d = nullptr;
@@ -796,11 +897,26 @@ sdrgpu_status upload_selection(sdrgpu_channelizer *h)
         SDRGPU_CUDA(cudaMemcpy(h->d_post_state, init.data(), sizeof(PostState) * init.size(), cudaMemcpyHostToDevice));
     }
     if (n_two > 0) SDRGPU_CUDA(cudaMalloc(&h->d_out2, sizeof(float) * 2 * (size_t)h->max_blocks * (size_t)n_two));
+    if (!mix.empty()) {
+        if (!h->osc_stream) {
+            SDRGPU_CUDA(cudaStreamCreateWithFlags(&h->osc_stream, cudaStreamNonBlocking));
+            SDRGPU_CUDA(cudaEventCreateWithFlags(&h->ev_mix, cudaEventDisableTiming));
+            SDRGPU_CUDA(cudaEventCreateWithFlags(&h->ev_osc, cudaEventDisableTiming));
+        }
+        h->osc_ring_len = (h->max_blocks + 8 + 1) & ~1;   // even: the producer stores pairs
+        std::vector<float2> start(mix.size(), make_float2(0.0f, -1.0f));   // Oscillator.java:24
+        SDRGPU_CUDA(cudaMalloc(&h->d_mix, sizeof(MixChannel) * mix.size()));
+        SDRGPU_CUDA(cudaMalloc(&h->d_mix_state, sizeof(float2) * mix.size()));
+        SDRGPU_CUDA(cudaMalloc(&h->d_osc, sizeof(float2) * mix.size() * (size_t)h->osc_ring_len));
+        SDRGPU_CUDA(cudaMemcpy(h->d_mix, mix.data(), sizeof(MixChannel) * mix.size(), cudaMemcpyHostToDevice));
+        SDRGPU_CUDA(cudaMemcpy(h->d_mix_state, start.data(), sizeof(float2) * mix.size(), cudaMemcpyHostToDevice));
+    }
+    h->n_mix = (int)mix.size();
     h->n_sel = n;
     h->n_rows = rows;
     h->n_post = (int)post.size();
     h->gain_exact = exact;
-    h->identity = exact && n == h->M && post.empty();
+    h->identity = exact && n == h->M && post.empty() && mix.empty();
     for (int i = 0; i < n && h->identity; i++)
         if (sel[i] != i || gf[i] != gf[0]) h->identity = 0;
     h->gain_uniform = n > 0 ? gf[0] : 0.0f;
@@ -915,6 +1031,41 @@ sdrgpu_status sdrgpu::chan_enqueue(sdrgpu_channelizer *h, const float2 *d_in, in
             post_channel_kernel<<<h->n_post, 32, 0, h->stream>>>(d_out, stride, h->d_out2, 2LL * h->max_blocks, n_blocks, h->d_post,
                                                                  h->d_post_state, h->synth);
             count_launch();
+            SDRGPU_CUDA(cudaGetLastError());
+        }
+        if (layout == SDRGPU_LAYOUT_CHANNELS && h->n_mix > 0) {
+            if (n_blocks > h->osc_ring_len) return fail(SDRGPU_ERR_OVERFLOW, "%d blocks exceed the oscillator look-ahead", n_blocks);
+            const int pgrid = (h->n_mix + 31) / 32;
+            const long long have = h->osc_produced - h->osc_consumed;
+            // wait for the top-up in flight only if this call reaches into what it writes (or has to produce itself)
+            if (h->osc_pending && (h->osc_consumed + n_blocks > h->osc_safe || have < n_blocks)) {
+                SDRGPU_CUDA(cudaStreamWaitEvent(h->stream, h->ev_osc, 0));
+                h->osc_pending = false;
+                h->osc_safe = h->osc_produced;
+            }
+            if (have < n_blocks) {  // first call, or a call longer than the look-ahead: produce the rest in line
+                osc_produce_kernel<<<pgrid, 32, 0, h->stream>>>(h->d_mix, h->d_mix_state, h->d_osc, h->osc_ring_len,
+                                                               h->osc_produced, (int)(n_blocks - have), h->n_mix);
+                h->osc_produced += n_blocks - have;
+                h->osc_safe = h->osc_produced;
+                count_launch();
+            }
+            osc_mix_kernel<<<dim3((n_blocks + 255) / 256, h->n_mix), 256, 0, h->stream>>>(d_out, stride, h->d_mix, h->d_osc,
+                                                                                          h->osc_ring_len, h->osc_consumed, n_blocks);
+            count_launch();
+            h->osc_consumed += n_blocks;
+            // top the ring up to a call's worth on the side stream, behind the mix that has just read it
+            const int top_up = h->max_blocks - (int)(h->osc_produced - h->osc_consumed);
+            if (top_up > 0) {
+                SDRGPU_CUDA(cudaEventRecord(h->ev_mix, h->stream));
+                SDRGPU_CUDA(cudaStreamWaitEvent(h->osc_stream, h->ev_mix, 0));
+                osc_produce_kernel<<<pgrid, 32, 0, h->osc_stream>>>(h->d_mix, h->d_mix_state, h->d_osc, h->osc_ring_len,
+                                                                    h->osc_produced, top_up, h->n_mix);
+                SDRGPU_CUDA(cudaEventRecord(h->ev_osc, h->osc_stream));
+                h->osc_produced += top_up;
+                h->osc_pending = true;
+                count_launch();
+            }
             SDRGPU_CUDA(cudaGetLastError());
         }
     }
@@ -1122,6 +1273,15 @@ sdrgpu_status sdrgpu_chan_destroy(sdrgpu_channelizer *h)
     cudaFree(h->d_post);
     cudaFree(h->d_post_state);
     cudaFree(h->d_out2);
+    if (h->osc_stream) {
+        cudaStreamSynchronize(h->osc_stream);
+        cudaStreamDestroy(h->osc_stream);
+        cudaEventDestroy(h->ev_mix);
+        cudaEventDestroy(h->ev_osc);
+    }
+    cudaFree(h->d_mix);
+    cudaFree(h->d_mix_state);
+    cudaFree(h->d_osc);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     if (h->copy_in) cudaStreamDestroy(h->copy_in);
     if (h->copy_out) cudaStreamDestroy(h->copy_out);

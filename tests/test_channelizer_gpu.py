@@ -237,6 +237,38 @@ def test_frequency_offset_and_two_channel_output_processors(gpu):
         ch.setOutputChannels([([1, 2, 3], 0)])
 
 
+def test_frequency_corrected_channels_oscillator_look_ahead_is_bit_exact(gpu):
+    """One-bin channels with an offset take their oscillator values from a ring that a side-stream kernel fills ahead of
+    use.  Fed the GPU's own uncorrected rows, the oracle's Oscillator + applyGain must reproduce every corrected row bit
+    for bit, across many ragged calls (ring wrap-around, calls longer than the look-ahead left in the ring, empty calls)."""
+    from sdrtrunk_b200.dsp import ComplexPolyphaseChannelizerM2
+    m, fs = 96, 2.4e6
+    rng = np.random.default_rng(23)
+    taps = oracle.sinc_m2_channelizer(25000.0, m, 9)
+    n = 48 * 3000
+    x = sg.interleave(sg.awgn(rng, n, 0.1))
+    bins_offsets = [(7, 900), (3, -12000), (50, 1), (95, 6250), (20, -3333)]
+    max_floats = 2 * 48 * 400                              # look-ahead of 400 blocks: the stream below wraps it many times
+    plain = ComplexPolyphaseChannelizerM2(taps, int(fs), m, maxInputFloats=max_floats)
+    plain.setChannels([b for b, _ in bins_offsets], gain=1.0)
+    corr = ComplexPolyphaseChannelizerM2(taps, int(fs), m, maxInputFloats=max_floats)
+    corr.setOutputChannels([([b], off, 96.0) for b, off in bins_offsets])
+    oscs = [oracle.Oscillator(off, 50000.0) for _, off in bins_offsets]
+    pos = 0
+    sizes = [400, 1, 399, 400, 0, 17, 400, 250, 400, 400, 83]
+    while pos < n:
+        for blocks in sizes:
+            cut = min(x.size, 2 * (pos + 48 * blocks))
+            rows = plain.receiveChannels(x[2 * pos:cut])
+            got = corr.receiveChannels(x[2 * pos:cut])
+            for i, o in enumerate(oscs):
+                want = oracle.apply_gain(o.mix(rows[i]), 96.0)
+                assert np.array_equal(got[i], want), (pos, i)
+            pos = cut // 2
+            if pos >= n:
+                break
+
+
 @pytest.mark.parametrize("fmt", ["u8", "s8", "s16le"])
 def test_native_tuner_sample_formats(gpu, fmt):
     """section 8f #1: ByteSampleConverter / SignedByteSampleConverter / 16-bit conversion on the device, standalone
