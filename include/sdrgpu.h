@@ -287,7 +287,8 @@ enum {
 };
 sdrgpu_status sdrgpu_bank_set_sync_detector(sdrgpu_bank *b, int kind);
 /* Tuning: how many lanes of a warp work on one channel in the symbol demodulator kernel -- 32 (one warp per channel),
- * 16 (two channels per warp), 1 (one thread per channel), 0 = chosen from the bank size (default).  All variants do
+ * 16 (two channels per warp), 8 / 4 (four / eight channels per warp; not with SDRGPU_SYNC_P25_PHASE1 / _PHASE2),
+ * 1 (one thread per channel), 0 = chosen from the bank size (default).  All variants do
  * the same arithmetic on the same per-channel state; the result does not depend on the choice, which may change
  * between calls -- except while a sync detector (SDRGPU_SYNC_P25_PHASE1 / _PHASE2) is enabled: choose the layout first
  * (SDRGPU_ERR_BAD_STATE otherwise). */
@@ -314,6 +315,23 @@ sdrgpu_status sdrgpu_pipeline_set_chunks(sdrgpu_pipeline *p, int chunks);
 sdrgpu_status sdrgpu_pipeline_process(sdrgpu_pipeline *p, const void *iq, int n_floats, int in_mem,
                                       uint8_t *symbols, int symbol_stride, float *demod,
                                       long long demod_stride_floats, int *counts, int out_mem);
+
+/* Several tuners, one bank.  In the reference every channel is its own task (TunerChannelSource.processSamples,
+ * J/source/tuner/channel/TunerChannelSource.java:290-319, scheduled per channel by
+ * PolyphaseChannelManager.java:582-623), whichever tuner it came from.  The symbol demodulator is serial per
+ * channel, so one tuner's few hundred channels leave most of the GPU idle: a multi-tuner pipeline lets n_chans
+ * channelizers (equal channel counts) write consecutive row ranges of ONE bank -- bank rows
+ * [sum of the selections before k, ...) belong to chans[k] -- and the filter / demodulator kernels run once over all of
+ * them.  iq[k] is tuner k's buffer (every tuner delivers n_floats values per call, in its channelizer's input
+ * format); outputs are indexed by bank row.  Results are identical to n_chans single-tuner pipelines. */
+sdrgpu_status sdrgpu_pipeline_create_multi(sdrgpu_pipeline **p, sdrgpu_channelizer *const *chans, int n_chans,
+                                           sdrgpu_bank *bank);
+sdrgpu_status sdrgpu_pipeline_process_multi(sdrgpu_pipeline *p, const void *const *iq, int n_floats, int in_mem,
+                                            uint8_t *symbols, int symbol_stride, float *demod,
+                                            long long demod_stride_floats, int *counts, int out_mem);
+/* time chunks for device-resident input (default 1: nothing to copy, but with many channels the latency-bound
+ * demodulator of chunk i overlaps the issue-bound channelizer / FIR kernels of chunk i+1) */
+sdrgpu_status sdrgpu_pipeline_set_device_chunks(sdrgpu_pipeline *p, int chunks);
 
 #ifdef __cplusplus
 }

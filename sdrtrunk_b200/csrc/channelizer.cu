@@ -966,6 +966,15 @@ sdrgpu_status sdrgpu::chan_enqueue(sdrgpu_channelizer *h, const float2 *d_in, in
     const int new_len = h->H + new_leftover;
     float2 *next = h->d_state[h->cur_state ^ 1];
     bool state_saved = false;
+    // checked before anything is launched or the framing state advances: a failing call leaves the handle as it was
+    if (n_blocks > 0 && (h->n_mix > 0 || h->n_post > 0)) {
+        // The reference rotates every channel's mixer for every buffer; the results layout has no per-channel rows to
+        // mix, and skipping the oscillators would leave them out of step with the sample stream for later calls.
+        if (layout != SDRGPU_LAYOUT_CHANNELS)
+            return fail(SDRGPU_ERR_BAD_STATE, "two-bin / frequency-corrected channels are selected: use SDRGPU_LAYOUT_CHANNELS");
+        if (h->n_mix > 0 && n_blocks > h->osc_ring_len)
+            return fail(SDRGPU_ERR_OVERFLOW, "%d blocks exceed the oscillator look-ahead", n_blocks);
+    }
     if (n_blocks > 0) {
         ChanParams p{};
         p.state = state;
@@ -1034,7 +1043,6 @@ sdrgpu_status sdrgpu::chan_enqueue(sdrgpu_channelizer *h, const float2 *d_in, in
             SDRGPU_CUDA(cudaGetLastError());
         }
         if (layout == SDRGPU_LAYOUT_CHANNELS && h->n_mix > 0) {
-            if (n_blocks > h->osc_ring_len) return fail(SDRGPU_ERR_OVERFLOW, "%d blocks exceed the oscillator look-ahead", n_blocks);
             const int pgrid = (h->n_mix + 31) / 32;
             const long long have = h->osc_produced - h->osc_consumed;
             // wait for the top-up in flight only if this call reaches into what it writes (or has to produce itself)
@@ -1144,6 +1152,7 @@ const float2 *sdrgpu::chan_convert(sdrgpu_channelizer *h, const void *iq_device,
     return h->d_in + first;
 }
 int sdrgpu::chan_half(const sdrgpu_channelizer *h) { return h->half; }
+int sdrgpu::chan_max_in(const sdrgpu_channelizer *h) { return h->max_in_complex; }
 
 
 extern "C" {
@@ -1365,7 +1374,15 @@ sdrgpu_status sdrgpu_chan_set_sample_rate(sdrgpu_channelizer *h, double sample_r
 {
     if (!h) return fail(SDRGPU_ERR_INVALID_ARG, "NULL handle");
     if (!(sample_rate > 0.0)) return fail(SDRGPU_ERR_INVALID_ARG, "sample rate must be positive");
+    const bool changed = sample_rate != h->sample_rate;
     h->sample_rate = sample_rate;
+    // the oscillator angles of frequency-corrected / two-bin channels depend on the channel rate: re-derive them
+    // (like Oscillator.setSampleRate -> update(); this restarts the oscillators, as selecting does)
+    if (changed && (h->n_mix > 0 || h->n_post > 0)) {
+        SDRGPU_CUDA(cudaSetDevice(h->device));
+        SDRGPU_CUDA(cudaStreamSynchronize(h->stream));
+        return upload_selection(h);
+    }
     return SDRGPU_OK;
 }
 

@@ -144,7 +144,7 @@ class Bank:
         native.check(native.lib().sdrgpu_bank_set_sync_detector(self._h, int(kind)))
 
     def setDemodulatorLanes(self, lanes):
-        """tuning / testing: 32, 16 or 1 lanes of a warp per channel in the demodulator kernel, 0 = automatic"""
+        """tuning / testing: 32, 16, 8, 4 or 1 lanes of a warp per channel in the demodulator kernel, 0 = automatic"""
         native.check(native.lib().sdrgpu_bank_set_demodulator_lanes(self._h, int(lanes)))
 
     def resetPLL(self, channel):
@@ -182,28 +182,42 @@ class Bank:
 
 
 class Pipeline:
-    """channelizer -> bank on the device (sdrgpu_pipeline): only dibits / demodulated floats come back."""
+    """channelizer(s) -> bank on the device (sdrgpu_pipeline): only dibits / demodulated floats come back.
+
+    `channelizer` may be a list of channelizers of equal channel count (several tuners): their selected channels are
+    consecutive row ranges of the one bank, and process() then takes one sample buffer per tuner
+    (sdrgpu_pipeline_create_multi: the reference runs every channel as its own task whichever tuner it came from,
+    J/source/tuner/channel/TunerChannelSource.java:290-319)."""
 
     def __init__(self, channelizer, bank):
-        self.channelizer, self.bank = channelizer, bank
+        self.channelizers = list(channelizer) if isinstance(channelizer, (list, tuple)) else [channelizer]
+        self.channelizer, self.bank = self.channelizers[0], bank
         self._h = C.c_void_p()
-        native.check(native.lib().sdrgpu_pipeline_create(C.byref(self._h), channelizer._h, bank._h))
+        handles = (C.c_void_p * len(self.channelizers))(*[c._h for c in self.channelizers])
+        native.check(native.lib().sdrgpu_pipeline_create_multi(C.byref(self._h), handles, len(self.channelizers), bank._h))
         self._pending = 0
 
     def setChunks(self, chunks):
         native.check(native.lib().sdrgpu_pipeline_set_chunks(self._h, int(chunks)))
 
+    def setDeviceChunks(self, chunks):
+        native.check(native.lib().sdrgpu_pipeline_set_device_chunks(self._h, int(chunks)))
+
     def process(self, samples, samples_mem=native.HOST, n_floats=None):
-        """samples: float32 interleaved tuner I/Q.  Returns per-channel dibit arrays (DQPSK) or demod floats."""
+        """samples: interleaved tuner I/Q in the channelizer's input format (one array, or one per tuner).  Returns
+        per-channel dibit arrays (DQPSK) or demod floats, indexed by bank row."""
         L = native.lib()
         bank = self.bank
+        multi = len(self.channelizers) > 1
+        bufs = list(samples) if multi else [samples]
+        assert len(bufs) == len(self.channelizers)
         if samples_mem == native.HOST:
-            samples = np.ascontiguousarray(samples, dtype=getattr(self.channelizer, "_dtype", np.float32))
-            n_floats = samples.size // 3 * 2 if getattr(self.channelizer, "_packed", False) else samples.size
-            in_ptr = native.ptr(samples)
+            bufs = [np.ascontiguousarray(b, dtype=getattr(self.channelizer, "_dtype", np.float32)) for b in bufs]
+            n_floats = bufs[0].size // 3 * 2 if getattr(self.channelizer, "_packed", False) else bufs[0].size
+            assert all(b.size == bufs[0].size for b in bufs)
         else:
-            in_ptr = native.ptr(samples)
             n_floats = int(n_floats)
+        in_ptrs = (C.c_void_p * len(bufs))(*[C.cast(native.ptr(b), C.c_void_p) for b in bufs])
         n = self.channelizer.blocksFor(n_floats)
         blocks = (self._pending + n) // bank.block_size
         n_out = blocks * (bank.block_size // max(bank.decimation, 1))
@@ -212,13 +226,13 @@ class Pipeline:
         if bank.is_dqpsk:
             stride = max(16, n_out // 3 + 16)
             symbols = np.zeros((bank.n_channels, stride), np.uint8)
-            native.check(L.sdrgpu_pipeline_process(self._h, in_ptr, n_floats, samples_mem, native.ptr(symbols), stride,
-                                                   None, 0, native.ptr(counts), native.HOST))
+            native.check(L.sdrgpu_pipeline_process_multi(self._h, in_ptrs, n_floats, samples_mem, native.ptr(symbols), stride,
+                                                         None, 0, native.ptr(counts), native.HOST))
             return [symbols[c, :counts[c]].copy() for c in range(bank.n_channels)]
         width = n_out if bank.is_fm else 2 * n_out
         dem = np.zeros((bank.n_channels, max(width, 1)), np.float32)
-        native.check(L.sdrgpu_pipeline_process(self._h, in_ptr, n_floats, samples_mem, None, 0, native.ptr(dem),
-                                               dem.shape[1], native.ptr(counts), native.HOST))
+        native.check(L.sdrgpu_pipeline_process_multi(self._h, in_ptrs, n_floats, samples_mem, None, 0, native.ptr(dem),
+                                                     dem.shape[1], native.ptr(counts), native.HOST))
         return dem[:, :width]
 
     def dispose(self):

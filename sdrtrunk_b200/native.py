@@ -121,6 +121,9 @@ PROTOTYPES = {
     "sdrgpu_bank_last_kernel_ms": (C.c_int, [_vp, _f32p]),
     "sdrgpu_pipeline_create": (C.c_int, [_vpp, _vp, _vp]),
     "sdrgpu_pipeline_set_chunks": (C.c_int, [_vp, C.c_int]),
+    "sdrgpu_pipeline_set_device_chunks": (C.c_int, [_vp, C.c_int]),
+    "sdrgpu_pipeline_create_multi": (C.c_int, [_vpp, _vp, C.c_int, _vp]),
+    "sdrgpu_pipeline_process_multi": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, C.c_int, _vp, C.c_longlong, _vp, C.c_int]),
     "sdrgpu_pipeline_destroy": (C.c_int, [_vp]),
     "sdrgpu_pipeline_process": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, C.c_int, _vp, C.c_longlong, _vp, C.c_int]),
 }

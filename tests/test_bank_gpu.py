@@ -63,11 +63,12 @@ def test_fir_streaming_ragged_calls(gpu):
         assert np.array_equal(got[k], oracle.ComplexFIR(taps).filter(x[k]))
 
 
-@pytest.mark.parametrize("rate", [2, 4, 8, 16, 32, 64])
+@pytest.mark.parametrize("rate", [2, 4, 8, 16, 32, 64, 128, 256, 512, 1024])
 def test_decimation_cascade_bit_exact(gpu, rate):
+    """every rate DecimationFilterFactory.getComplexDecimationFilter offers (DecimationFilterFactory.java:36-104)"""
     from sdrtrunk_b200.dsp import Bank
     rng = np.random.default_rng(rate)
-    c, n = 4, 4096
+    c, n = 4, max(4096, 4 * rate)
     x = _noise(rng, c, 2 * n)
     bank = Bank(c, 50000.0 * rate, decimation=rate, block_size=n, max_samples_per_call=n)
     got = np.concatenate([bank.process(x[:, :2 * n]), bank.process(x[:, 2 * n:])], axis=1)
@@ -411,28 +412,35 @@ def test_sync_detector_thread_per_channel_kernel(gpu):
         assert np.array_equal(np.concatenate([got[k], got2[k]]), want[k % len(offsets)]), k
 
 
-@pytest.mark.parametrize("c,lanes", [(1024, 0), (3072, 0), (4608, 0), (321, 16), (97, 1), (64, 32)])
+def _scattered(c, distinct):
+    """signal index of every bank row: neighbouring rows, rows 32 / 64 apart (a warp / a block later) and rows one
+    kernel tile apart all carry different signals, so a demodulator or filter that reads another row's samples fails"""
+    r = np.arange(c)
+    return (r * 37 + (r // distinct) * 11 + (r // 1024) * 5) % distinct
+
+
+@pytest.mark.parametrize("c,lanes", [(1024, 0), (3072, 0), (4608, 0), (321, 16), (97, 1), (64, 32), (1500, 8), (203, 8),
+                                     (2100, 4), (77, 4)])
 def test_many_channels(gpu, c, lanes):
-    """BASELINE config 4 shape: >= 1000 channel-domain streams; every channel gets the same input so that one
-    oracle run checks all of them.  By bank size the demodulator runs one warp per channel (1024), two channels per
-    warp (3072) or one thread per channel (4608); the forced layouts use odd channel counts (a last warp with an idle
-    half / idle lanes)."""
+    """BASELINE config 4 shape: >= 1000 channel-domain streams.  64 distinct HDQPSK signals (own dibits, carrier offset,
+    timing phase and noise) are scattered over the rows and EVERY row is compared with the oracle's decode of the signal
+    it carries.  By bank size the demodulator runs one warp per channel (1024), two channels per warp (3072) or one
+    thread per channel (4608); the forced layouts use odd channel counts (a last warp with idle lanes)."""
     from sdrtrunk_b200.dsp import Bank
     rng = np.random.default_rng(8)
-    n = 4 * 1024
-    sig, _ = _p25_signal("hdqpsk", rng, n, 0)
-    alt, _ = _p25_signal("hdqpsk", rng, n, 1)
-    x = np.tile(sig, (c, 1))
-    odd = min(777, c - 1)
-    x[odd] = alt
+    n, distinct = 4 * 1024, 64
+    sigs = [_p25_signal("hdqpsk", rng, n, k)[0] for k in range(distinct)]
+    which = _scattered(c, distinct)
+    assert all(which[k] != which[k + 1] for k in range(c - 1)) and all(which[k] != which[k + 32] for k in range(c - 32))
+    x = np.stack(sigs)[which]
     taps = hdqpsk_taps()
     bank = Bank.preset(gpu.PRESET_P25_HDQPSK, c, 50000.0, taps, max_samples_per_call=n)
     bank.setDemodulatorLanes(lanes)
     got = [np.concatenate(parts) for parts in zip(bank.process(x[:, :2 * 3072]), bank.process(x[:, 2 * 3072:]))]
-    want = oracle.P25Chain(oracle.HDQPSK, 50000.0, taps).receive(sig)
-    want_alt = oracle.P25Chain(oracle.HDQPSK, 50000.0, taps).receive(alt)
+    want = [oracle.P25Chain(oracle.HDQPSK, 50000.0, taps).receive(sig) for sig in sigs]
+    assert len({w.tobytes() for w in want}) == distinct          # the decodes differ, so a swapped row is visible
     for k in range(c):
-        assert np.array_equal(got[k], want_alt if k == odd else want), k
+        assert np.array_equal(got[k], want[which[k]]), k
 
 
 def test_demodulator_layout_can_change_between_calls(gpu):
@@ -446,11 +454,11 @@ def test_demodulator_layout_can_change_between_calls(gpu):
     bank = Bank.preset(gpu.PRESET_P25_C4FM, 5, 50000.0, taps, max_samples_per_call=n)
     bank.setSyncDetector(gpu.SYNC_P25_PHASE2_FRAMED)      # the framer's state is layout independent as well
     parts = []
-    for i, lanes in enumerate((32, 16, 1, 16, 32, 1, 0, 16)):
+    for i, lanes in enumerate((32, 16, 1, 8, 32, 4, 0, 16)):
         bank.setDemodulatorLanes(lanes)
         parts.append(bank.process(x[:, 2 * 1024 * i:2 * 1024 * (i + 1)]))
     with pytest.raises(gpu.IllegalArgumentException):
-        bank.setDemodulatorLanes(8)
+        bank.setDemodulatorLanes(7)
     for k in range(5):
         chain = oracle.P25Chain(oracle.C4FM, 50000.0, taps)
         chain.attach_sync(oracle.SYNC_P25_PHASE2_FRAMED, 50000.0)
@@ -459,6 +467,8 @@ def test_demodulator_layout_can_change_between_calls(gpu):
     bank.setSyncDetector(gpu.SYNC_P25_PHASE1)
     with pytest.raises(gpu.IllegalStateException):
         bank.setDemodulatorLanes(1)
+    with pytest.raises(gpu.IllegalStateException):
+        bank.setDemodulatorLanes(8)                         # the batched sync matcher needs 16 lanes per channel
 
 
 # ------------------------------------------------------------------------------------------------ pipeline
@@ -712,3 +722,202 @@ def test_handles_are_independent_across_host_threads(gpu):
             t.join()
         for i in range(4):
             assert all(np.array_equal(a, b) for a, b in zip(got[i], want[i])), i
+
+
+# ------------------------------------------------------------------------------------------------ several tuners, one bank
+def _tuner_stream(rng, m, n_ch, bins, kind="c4fm"):
+    base = [sg.c4fm(rng.integers(0, 4, int(n_ch * 0.096) + 8), carrier_offset=rng.uniform(-200, 200),
+                    timing_phase=rng.uniform(0, 1), n_samples=n_ch, amplitude=0.05) for _ in bins]
+    return sg.interleave(sg.multiplex(base, bins, m, n_ch) + sg.awgn(rng, n_ch * m // 2, 1e-3))
+
+
+@pytest.mark.parametrize("fmt", ["f32", "s8"])
+def test_multi_tuner_pipeline_equals_single_tuner_pipelines(gpu, fmt):
+    """sdrgpu_pipeline_create_multi: three tuners' channelizers feed consecutive row ranges of one bank; the dibits of
+    every row equal those of three separate single-tuner pipelines (and so the oracle's), for the chunked host path, the
+    single pass, device-resident input with and without time chunks, and ragged calls."""
+    import ctypes as C
+    from sdrtrunk_b200.dsp import Bank, ComplexPolyphaseChannelizerM2, Pipeline
+    m, n_ch = 96, 12 * 1024
+    rng = np.random.default_rng(71)
+    bins = [[2, 30, 77], [5, 6], [0, 47, 48, 95]]
+    xs = [_tuner_stream(rng, m, n_ch, b) for b in bins]
+    if fmt == "s8":
+        xs = [np.clip(np.round(x * 128.0 * 4), -128, 127).astype(np.int8) for x in xs]
+    taps, fir = oracle.sinc_m2_channelizer(25000.0, m, 9), c4fm_taps()
+    rows = sum(len(b) for b in bins)
+
+    def chan_for(k):
+        ch = ComplexPolyphaseChannelizerM2(taps, 2400000, m, maxInputFloats=xs[0].size)
+        ch.setChannels(bins[k])
+        ch.setSampleFormat(fmt)
+        return ch
+
+    want = []
+    for k in range(3):
+        pipe = Pipeline(chan_for(k), Bank.preset(gpu.PRESET_P25_C4FM, len(bins[k]), 50000.0, fir, max_samples_per_call=n_ch))
+        pipe.setChunks(1)
+        want += pipe.process(xs[k])
+    assert len(want) == rows and all(w.size > 1000 for w in want)
+    if fmt == "f32":   # ... and the single-tuner reference is the oracle's decode of the same channel I/Q
+        iq = chan_for(1).receiveChannels(xs[1])
+        assert np.array_equal(want[3], oracle.P25Chain(oracle.C4FM, 50000.0, fir).receive(iq[0]))
+
+    def multi(chunks, device_chunks=1, device_input=False, cuts=()):
+        pipe = Pipeline([chan_for(k) for k in range(3)], Bank.preset(gpu.PRESET_P25_C4FM, rows, 50000.0, fir,
+                                                                     max_samples_per_call=n_ch))
+        pipe.setChunks(chunks)
+        pipe.setDeviceChunks(device_chunks)
+        edges = [0] + [c // 2 * 2 for c in cuts] + [xs[0].size]
+        parts = []
+        for a, b in zip(edges[:-1], edges[1:]):
+            seg = [x[a:b] for x in xs]
+            if not device_input:
+                parts.append(pipe.process(seg))
+                continue
+            L = gpu.lib()
+            ptrs = []
+            for s_ in seg:
+                d = C.c_void_p()
+                gpu.check(L.sdrgpu_device_alloc(C.byref(d), max(s_.nbytes, 16)))
+                gpu.check(L.sdrgpu_memcpy(d, gpu.ptr(np.ascontiguousarray(s_)), s_.nbytes, gpu.DEVICE, gpu.HOST))
+                ptrs.append(d)
+            parts.append(pipe.process([d.value for d in ptrs], gpu.DEVICE, seg[0].size))
+            for d in ptrs:
+                L.sdrgpu_device_free(d)
+        return [np.concatenate(p) for p in zip(*parts)]
+
+    for kw in (dict(chunks=8), dict(chunks=1), dict(chunks=3, cuts=(xs[0].size // 3, xs[0].size // 3 + 4000)),
+               dict(chunks=1, device_input=True), dict(chunks=1, device_chunks=4, device_input=True)):
+        got = multi(**kw)
+        assert len(got) == rows
+        for r in range(rows):
+            assert np.array_equal(got[r], want[r]), (kw, r)
+
+
+def test_multi_tuner_pipeline_argument_checks(gpu):
+    import ctypes as C
+    from sdrtrunk_b200.dsp import Bank, ComplexPolyphaseChannelizerM2, Pipeline
+    taps, fir = oracle.sinc_m2_channelizer(25000.0, 96, 9), c4fm_taps()
+    a = ComplexPolyphaseChannelizerM2(taps, 2400000, 96, maxInputFloats=96 * 2048)
+    b = ComplexPolyphaseChannelizerM2(taps, 2400000, 96, maxInputFloats=96 * 2048)
+    a.setChannels([1, 2])
+    b.setChannels([3])
+    with pytest.raises(gpu.IllegalArgumentException):      # 3 rows selected, bank has 4
+        Pipeline([a, b], Bank.preset(gpu.PRESET_P25_C4FM, 4, 50000.0, fir, max_samples_per_call=2048))
+    other = ComplexPolyphaseChannelizerM2(oracle.sinc_m2_channelizer(25000.0, 80, 9), 2000000, 80)
+    other.setChannels([3])
+    with pytest.raises(gpu.IllegalArgumentException):      # different channel counts cannot share a bank
+        Pipeline([a, other], Bank.preset(gpu.PRESET_P25_C4FM, 3, 50000.0, fir, max_samples_per_call=2048))
+    pipe = Pipeline([a, b], Bank.preset(gpu.PRESET_P25_C4FM, 3, 50000.0, fir, max_samples_per_call=2048))
+    x = np.zeros(96 * 1024, np.float32)
+    a.receiveChannels(x[:96])                               # tuner a is now 48 samples ahead of tuner b
+    with pytest.raises(gpu.IllegalStateException):
+        pipe.process([x, x])
+
+
+def test_pipeline_oversized_and_null_input_is_rejected_before_any_copy(gpu):
+    """the chunked host path drives the channelizer internals directly, so it has to make sdrgpu_chan_process's
+    checks itself: a bank sized larger than the channelizer's max_input_floats must give OVERFLOW, not a copy past the
+    end of the channelizer's staging."""
+    import ctypes as C
+    from sdrtrunk_b200.dsp import Bank, ComplexPolyphaseChannelizerM2, Pipeline
+    m = 96
+    taps, fir = oracle.sinc_m2_channelizer(25000.0, m, 9), c4fm_taps()
+    chan = ComplexPolyphaseChannelizerM2(taps, 2400000, m, maxInputFloats=2 * 48 * 2048)     # 2048 blocks per call
+    chan.setChannels([4, 9])
+    pipe = Pipeline(chan, Bank.preset(gpu.PRESET_P25_C4FM, 2, 50000.0, fir, max_samples_per_call=16 * 1024))
+    pipe.setChunks(8)
+    big = np.zeros(2 * 48 * 8192, np.float32)
+    with pytest.raises(gpu.OverflowError_):
+        pipe.process(big)
+    L = gpu.lib()
+    counts = np.zeros(2, np.int32)
+    sym = np.zeros((2, 4096), np.uint8)
+    st = L.sdrgpu_pipeline_process(pipe._h, None, 2 * 48 * 2048, gpu.HOST, gpu.ptr(sym), 4096, None, 0, gpu.ptr(counts), gpu.HOST)
+    assert st == gpu.ERR_INVALID_ARG
+    # the handle is still usable and in its reset state
+    x = _tuner_stream(np.random.default_rng(5), m, 2048, [4, 9])
+    got = pipe.process(x)
+    ref = ComplexPolyphaseChannelizerM2(taps, 2400000, m, maxInputFloats=x.size)
+    ref.setChannels([4, 9])
+    iq = ref.receiveChannels(x)
+    for k in range(2):
+        assert np.array_equal(got[k], oracle.P25Chain(oracle.C4FM, 50000.0, fir).receive(iq[k]))
+
+
+def test_pipeline_host_input_device_output_does_not_keep_the_caller_pointer(gpu):
+    """sdrgpu.h promises that no caller pointer is kept after a call returns.  Chunked path, pinned host input,
+    DEVICE outputs: the input buffer is overwritten the moment the call returns, and the result must still be the one of
+    the original samples."""
+    import ctypes as C
+    from sdrtrunk_b200.dsp import Bank, ComplexPolyphaseChannelizerM2, Pipeline
+    m, n_ch = 96, 16 * 1024
+    rng = np.random.default_rng(73)
+    bins = [2, 30, 77]
+    x = _tuner_stream(rng, m, n_ch, bins)
+    taps, fir = oracle.sinc_m2_channelizer(25000.0, m, 9), c4fm_taps()
+    L = gpu.lib()
+
+    def build():
+        chan = ComplexPolyphaseChannelizerM2(taps, 2400000, m, maxInputFloats=x.size)
+        chan.setChannels(bins)
+        pipe = Pipeline(chan, Bank.preset(gpu.PRESET_P25_C4FM, len(bins), 50000.0, fir, max_samples_per_call=n_ch))
+        pipe.setChunks(8)
+        return pipe
+
+    want = build().process(x)
+    pinned = C.c_void_p()
+    gpu.check(L.sdrgpu_alloc_pinned(C.byref(pinned), x.nbytes))
+    host = np.ctypeslib.as_array(C.cast(pinned, C.POINTER(C.c_float)), shape=(x.size,))
+    stride = 4096
+    d_sym, d_cnt = C.c_void_p(), C.c_void_p()
+    gpu.check(L.sdrgpu_device_alloc(C.byref(d_sym), len(bins) * stride))
+    gpu.check(L.sdrgpu_device_alloc(C.byref(d_cnt), 4 * len(bins)))
+    for _ in range(3):
+        pipe = build()
+        host[:] = x
+        gpu.check(L.sdrgpu_pipeline_process(pipe._h, pinned, x.size, gpu.HOST, d_sym, stride, None, 0, d_cnt, gpu.DEVICE))
+        host[:] = 7.0                                         # the caller reuses its buffer right away
+        pipe.bank.sync()
+        sym = np.zeros((len(bins), stride), np.uint8)
+        cnt = np.zeros(len(bins), np.int32)
+        gpu.check(L.sdrgpu_memcpy(gpu.ptr(sym), d_sym, sym.nbytes, gpu.HOST, gpu.DEVICE))
+        gpu.check(L.sdrgpu_memcpy(gpu.ptr(cnt), d_cnt, cnt.nbytes, gpu.HOST, gpu.DEVICE))
+        for k in range(len(bins)):
+            assert cnt[k] == want[k].size and np.array_equal(sym[k, :cnt[k]], want[k]), k
+    L.sdrgpu_device_free(d_sym)
+    L.sdrgpu_device_free(d_cnt)
+    L.sdrgpu_free_pinned(pinned)
+
+
+def test_config5_shape_800_channels_pipeline(gpu):
+    """BASELINE configs[4], one tuner: 20 MS/s, M = 800, every bin carries C4FM, all 800 channels through the fused
+    pipeline (pfb2_kernel<800, 32, 25> direct row stores -> FIR -> AGC -> demodulator).  Every channel must decode its
+    transmitted dibits, and a sample of rows -- first / last, both sides of the 32 x 25 factorisation's row groups, the
+    spectrum edge -- is bit-exact against the oracle chain fed the same channel I/Q, whose channel I/Q in turn is within
+    1e-4 of the oracle channelizer's."""
+    from sdrtrunk_b200.dsp import Bank, ComplexPolyphaseChannelizerM2, Pipeline
+    m, n_ch = 800, 4 * 1024
+    rng = np.random.default_rng(46)
+    dibs = [rng.integers(0, 4, int(n_ch * 0.096) + 8) for _ in range(m)]
+    base = [sg.c4fm(dibs[k], carrier_offset=rng.uniform(-200, 200), timing_phase=rng.uniform(0, 1), n_samples=n_ch,
+                    amplitude=0.01, phase0=rng.uniform(0, 6.28)) for k in range(m)]
+    x = sg.interleave(sg.multiplex(base, list(range(m)), m, n_ch) + sg.awgn(rng, n_ch * m // 2, 1e-3))
+    fir = c4fm_taps()
+    chan = ComplexPolyphaseChannelizerM2(2e7, 9, maxInputFloats=x.size)
+    assert chan.getChannelCount(2e7) == 800
+    pipe = Pipeline(chan, Bank.preset(gpu.PRESET_P25_C4FM, m, 50000.0, fir, max_samples_per_call=n_ch))
+    got = pipe.process(x)
+    assert len(got) == m
+    scores = np.array([_score(got[k], dibs[k], skip=150) for k in range(m)])
+    assert np.mean(scores > 0.97) > 0.95, np.sort(scores)[:10]
+    slow = [int(k) for k in np.nonzero(scores <= 0.97)[0]][:8]
+    iq = ComplexPolyphaseChannelizerM2(2e7, 9, maxInputFloats=x.size).receiveChannels(x)
+    head = 512                                                  # blocks of the (slow) float64-DFT oracle channelizer
+    res = oracle.Channelizer(oracle.sinc_m2_channelizer(25000.0, m, 9), m).receive(x[:2 * head * (m // 2)], mode="f64")
+    for k in [0, 1, 24, 25, 31, 32, 399, 400, 401, 767, 768, 799] + slow:
+        want = oracle.P25Chain(oracle.C4FM, 50000.0, fir).receive(iq[k])
+        assert np.array_equal(got[k], want), k
+        y = oracle.OneChannelOutputProcessor(50000.0, k, float(m)).process(res)
+        assert sg.rel_rms(iq[k][:2 * head], y) < TOL, k

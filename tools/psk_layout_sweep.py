@@ -26,10 +26,11 @@ def main():
         z = sg.c4fm(dib, carrier_offset=rng.uniform(-200, 200), timing_phase=rng.uniform(0, 1), n_samples=n)
         base.append(sg.interleave(z + sg.awgn(rng, n, 0.03)))
     base = np.stack(base)
-    for c in (400, 800, 1200, 1600, 2048, 3072, 4096, 6144):
+    counts = [int(a) for a in sys.argv[1:]] or [400, 800, 1200, 1600, 2400, 3200, 4800, 6400]
+    for c in counts:
         x = np.tile(base, (c // 8, 1))
         row = []
-        for lanes in (32, 16, 1):
+        for lanes in (32, 16, 8, 4, 1):
             bank = Bank.preset(native.PRESET_P25_C4FM, c, 50000.0, fir, max_samples_per_call=n)
             bank.setDemodulatorLanes(lanes)
             bank.enableTiming(True)
@@ -39,7 +40,8 @@ def main():
                 best = min(best, bank.lastKernelMs()[1])
             row.append(best)
             bank.dispose()
-        print("%5d channels: 32 lanes %.3f ms, 16 lanes %.3f ms, 1 lane %.3f ms" % (c, *row), flush=True)
+        print("%5d channels: 32 lanes %.3f ms, 16 lanes %.3f ms, 8 lanes %.3f ms, 4 lanes %.3f ms, 1 lane %.3f ms" % (c, *row),
+              flush=True)
 
 
 if __name__ == "__main__":
