@@ -1153,6 +1153,7 @@ const float2 *sdrgpu::chan_convert(sdrgpu_channelizer *h, const void *iq_device,
 }
 int sdrgpu::chan_half(const sdrgpu_channelizer *h) { return h->half; }
 int sdrgpu::chan_max_in(const sdrgpu_channelizer *h) { return h->max_in_complex; }
+int sdrgpu::chan_leftover(const sdrgpu_channelizer *h) { return h->leftover; }
 
 
 extern "C" {

@@ -52,7 +52,8 @@ sdrgpu_status chan_upload(sdrgpu_channelizer *h, const void *iq, size_t first, i
 const float2 *chan_convert(sdrgpu_channelizer *h, const void *iq_device_or_null, size_t first, int n);
 size_t chan_complex_bytes(const sdrgpu_channelizer *h);   // bytes of one complex sample in the handle's input format
 int chan_half(const sdrgpu_channelizer *h);
-int chan_max_in(const sdrgpu_channelizer *h);   // complex samples one process call may carry (max_input_floats / 2)
+int chan_max_in(const sdrgpu_channelizer *h);
+int chan_leftover(const sdrgpu_channelizer *h);  // samples buffered that did not fill a block yet (mSampleBufferPointer)   // complex samples one process call may carry (max_input_floats / 2)
 
 // Airspy raw-sample converter (airspy.cu), stand-alone (sdrgpu_airspy_*) and as a channelizer input format
 sdrgpu_status airspy_create(sdrgpu_airspy **out, int max_samples);

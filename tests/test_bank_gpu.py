@@ -193,8 +193,10 @@ def _preset(gpu, kind):
             "dmr": (gpu.PRESET_DMR, oracle.DMR, c4fm_taps())}[kind]
 
 
+@pytest.mark.parametrize("lanes", [0, 8, 4, 2])
 @pytest.mark.parametrize("kind", ["c4fm", "lsm", "hdqpsk", "dmr"])
-def test_p25_bank_dibits_bit_exact(gpu, kind):
+def test_p25_bank_dibits_bit_exact(gpu, kind, lanes):
+    """lanes = 8 / 4 / 2: psk_multi_kernel (several samples of a period per lane, 4 / 8 / 16 channels per warp)"""
     from sdrtrunk_b200.dsp import Bank
     preset, okind, taps = _preset(gpu, kind)
     rng = np.random.default_rng({"c4fm": 21, "lsm": 22, "hdqpsk": 23, "dmr": 24}[kind])
@@ -203,6 +205,7 @@ def test_p25_bank_dibits_bit_exact(gpu, kind):
     x = np.stack([s[0] for s in sigs])
     x[5] *= 1e-3                                    # AGC brings a weak channel up
     bank = Bank.preset(preset, c, 50000.0, taps, max_samples_per_call=8 * 1024)
+    bank.setDemodulatorLanes(lanes)
     parts = [bank.process(x[:, 2 * a:2 * b], want_filtered=True) for a, b in ((0, 8192), (8192, 9000), (9000, 17000), (17000, n))]
     for k in range(c):
         got = np.concatenate([p[0][k] for p in parts])
@@ -420,7 +423,7 @@ def _scattered(c, distinct):
 
 
 @pytest.mark.parametrize("c,lanes", [(1024, 0), (3072, 0), (4608, 0), (321, 16), (97, 1), (64, 32), (1500, 8), (203, 8),
-                                     (2100, 4), (77, 4)])
+                                     (2100, 4), (77, 4), (333, 2)])
 def test_many_channels(gpu, c, lanes):
     """BASELINE config 4 shape: >= 1000 channel-domain streams.  64 distinct HDQPSK signals (own dibits, carrier offset,
     timing phase and noise) are scattered over the rows and EVERY row is compared with the oracle's decode of the signal
@@ -811,7 +814,7 @@ def test_multi_tuner_pipeline_argument_checks(gpu):
         Pipeline([a, other], Bank.preset(gpu.PRESET_P25_C4FM, 3, 50000.0, fir, max_samples_per_call=2048))
     pipe = Pipeline([a, b], Bank.preset(gpu.PRESET_P25_C4FM, 3, 50000.0, fir, max_samples_per_call=2048))
     x = np.zeros(96 * 1024, np.float32)
-    a.receiveChannels(x[:96])                               # tuner a is now 48 samples ahead of tuner b
+    a.receiveChannels(x[:90])                               # tuner a is now 45 samples ahead of tuner b
     with pytest.raises(gpu.IllegalStateException):
         pipe.process([x, x])
 

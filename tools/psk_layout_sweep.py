@@ -30,7 +30,7 @@ def main():
     for c in counts:
         x = np.tile(base, (c // 8, 1))
         row = []
-        for lanes in (32, 16, 8, 4, 1):
+        for lanes in (32, 16, 8, 4, 2, 1):
             bank = Bank.preset(native.PRESET_P25_C4FM, c, 50000.0, fir, max_samples_per_call=n)
             bank.setDemodulatorLanes(lanes)
             bank.enableTiming(True)
@@ -40,7 +40,7 @@ def main():
                 best = min(best, bank.lastKernelMs()[1])
             row.append(best)
             bank.dispose()
-        print("%5d channels: 32 lanes %.3f ms, 16 lanes %.3f ms, 8 lanes %.3f ms, 4 lanes %.3f ms, 1 lane %.3f ms" % (c, *row),
+        print("%5d channels: 32 lanes %.3f ms, 16 lanes %.3f ms, 8x2 %.3f ms, 4x3 %.3f ms, 2x6 %.3f ms, 1 lane %.3f ms" % (c, *row),
               flush=True)
 
 
