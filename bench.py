@@ -107,14 +107,20 @@ def load_traffic(kernel):
 def fir_taps(demod):
     """decoder baseband filters: P25P1DecoderC4FM.java:136-148 (5100/6500 Hz, 72 taps at 50 kHz),
     P25P2DecoderHDQPSK.java:155-166 (6500/7200 Hz, 154 taps), NBFMDecoder.java:306-341 (5000/6250 Hz at 25 kHz, 45 taps)"""
-    import scipy.signal as ss
-    if demod == "c4fm":
-        return ss.remez(72, [0, 5100, 6500, 25000], [1, 0], fs=50000).astype(np.float32)
-    if demod == "hdqpsk":
-        return ss.remez(154, [0, 6500, 7200, 25000], [1, 0], fs=50000).astype(np.float32)
-    if demod == "nbfm":
-        return ss.remez(45, [0, 5000, 6250, 12500], [1, 0], fs=25000).astype(np.float32)
-    return None
+    # designed by the library's host-side restatement of the reference's RemezFIRFilterDesigner (csrc/remez.cpp): the taps
+    # the Java decoders run, not another Remez implementation's
+    from sdrtrunk_b200.dsp import FilterFactory, FIRFilterSpecification
+    spec = {"c4fm": (50000.0, 5100, 6500, 0.01, 0.01, None), "hdqpsk": (50000.0, 6500, 7200, 0.005, 0.01, None),
+            "nbfm": (50000.0, 10000, 12500, 0.01, 0.005, True)}.get(demod)
+    if spec is None:
+        return None
+    b = (FIRFilterSpecification.lowPassBuilder().sampleRate(spec[0]).passBandCutoff(spec[1]).passBandAmplitude(1.0)
+         .passBandRipple(spec[3]).stopBandAmplitude(0.0).stopBandStart(spec[2]).stopBandRipple(spec[4]))
+    if spec[5] is not None:
+        b = b.gridDensity(16).oddLength(spec[5])
+    taps = FilterFactory.getTaps(b.build())
+    assert taps is not None and taps.size == {"c4fm": 72, "hdqpsk": 154, "nbfm": 45}[demod]
+    return taps
 
 
 # ---------------------------------------------------------------------------------------------- clocks sampler

@@ -64,6 +64,18 @@ sdrgpu_status sdrgpu_design_sinc_m2_channelizer(double channel_bandwidth, int ch
 sdrgpu_status sdrgpu_design_sinc_m2_synthesizer(double channel_sample_rate, double channel_bandwidth, int channels,
                                                 int taps_per_channel, float *out, int capacity, int *n_taps);
 sdrgpu_status sdrgpu_design_half_band(int length, int window, float *out);
+/* The decoders' baseband low-pass filters: FIRFilterSpecification.lowPassBuilder()...build() + FilterFactory.getTaps
+ * (J/dsp/filter/fir/FIRFilterSpecification.java:381-428, J/dsp/filter/fir/remez/RemezFIRFilterDesigner.java:52-672,
+ * J/dsp/filter/FilterFactory.java:671-681).  Frequencies in Hz, ripples in dB as the builder takes them; order < 6 =
+ * estimate it (estimateFilterOrder, :909-937); odd_length: -1 = not requested, 0 / 1 = oddLength(false / true).
+ * P25P1DecoderC4FM.java:136-148 = (50000, 5100, 6500, 0.01, 0.01, 0, -1, 16) -> 72 taps; P25P2DecoderHDQPSK.java:155-166 =
+ * (50000, 6500, 7200, 0.005, 0.01, 0, -1, 16) -> 154 taps; NBFMDecoder.java:306-325 = (2 * 25000, 10000, 12500, 0.01,
+ * 0.005, 0, 1, 16) -> 45 taps.  SDRGPU_ERR_DESIGN where getTaps returns null (no convergence). */
+int sdrgpu_design_remez_estimate_order(double sample_rate, double frequency1, double frequency2, double pass_ripple_db,
+                                       double stop_ripple_db);
+sdrgpu_status sdrgpu_design_remez_low_pass(double sample_rate, double pass_band_end, double stop_band_start,
+                                           double pass_ripple_db, double stop_ripple_db, int order, int odd_length,
+                                           int grid_density, float *out, int capacity, int *n_taps);
 /* ComplexPolyphaseChannelizerM2.getChannelCount (J/dsp/filter/channelizer/ComplexPolyphaseChannelizerM2.java:148-161) */
 int sdrgpu_channel_count_for_rate(double sample_rate);
 

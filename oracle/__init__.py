@@ -52,6 +52,8 @@ def lib():
         "orc_sinc_m2_channelizer": (C.c_int, [C.c_double, C.c_int, C.c_int, _f32p, C.c_int]),
         "orc_sinc_m2_synthesizer": (C.c_int, [C.c_double, C.c_double, C.c_int, C.c_int, _f32p]),
         "orc_half_band": (C.c_int, [C.c_int, C.c_int, _f32p]),
+        "orc_remez_estimate_order": (C.c_int, [C.c_double] * 5),
+        "orc_remez_low_pass": (C.c_int, [C.c_double] * 5 + [C.c_int, C.c_int, C.c_int, _f32p, C.c_int]),
         "orc_fft_create": (vp, [C.c_int]),
         "orc_fft_destroy": (None, [vp]),
         "orc_ifft_f32": (None, [vp, _f32p]),
@@ -153,6 +155,40 @@ def half_band(length, window):
     if n < 0:
         raise ValueError("bad half-band length")
     return out
+
+
+def remez_estimate_order(sample_rate, f1, f2, pass_ripple_db, stop_ripple_db):
+    """FIRFilterSpecification.estimateFilterOrder"""
+    return lib().orc_remez_estimate_order(sample_rate, f1, f2, pass_ripple_db, stop_ripple_db)
+
+
+def remez_low_pass(sample_rate, pass_end, stop_start, pass_ripple_db, stop_ripple_db, order=0, odd_length=None,
+                   grid_density=16):
+    """FIRFilterSpecification.lowPassBuilder()...build() + FilterFactory.getTaps; None where getTaps returns null"""
+    out = np.zeros(4096, np.float32)
+    n = lib().orc_remez_low_pass(sample_rate, pass_end, stop_start, pass_ripple_db, stop_ripple_db, order,
+                                 -1 if odd_length is None else int(bool(odd_length)), grid_density,
+                                 out.ctypes.data_as(_f32p), out.size)
+    if n == -2:
+        raise ValueError("filter longer than 4096 taps")
+    return out[:n].copy() if n > 0 else None
+
+
+# the decoders' baseband filters, as the reference designs them
+def c4fm_baseband_taps():
+    """P25P1DecoderC4FM.getBasebandFilter (P25P1DecoderC4FM.java:136-148) at the 50 kHz channel rate"""
+    return remez_low_pass(50000.0, 5100, 6500, 0.01, 0.01)
+
+
+def hdqpsk_baseband_taps():
+    """P25P2DecoderHDQPSK.getBasebandFilter (P25P2DecoderHDQPSK.java:155-166)"""
+    return remez_low_pass(50000.0, 6500, 7200, 0.005, 0.01)
+
+
+def nbfm_iq_taps(decimated_sample_rate=25000.0, channel_bandwidth=12500.0):
+    """NBFMDecoder I/Q filter (NBFMDecoder.java:306-325): note sampleRate(decimatedSampleRate * 2)"""
+    return remez_low_pass(decimated_sample_rate * 2, int(channel_bandwidth * .8), int(channel_bandwidth), 0.01, 0.005,
+                          odd_length=True, grid_density=16)
 
 
 def window(kind, length):

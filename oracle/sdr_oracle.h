@@ -39,6 +39,13 @@ int orc_sinc_m2_channelizer(double channel_bandwidth, int channels, int taps_per
 int orc_sinc_m2_synthesizer(double channel_sample_rate, double channel_bandwidth, int channels,
                             int taps_per_channel, float *out);
 int orc_half_band(int length, int window_type, float *out);
+/* Remez / Parks-McClellan low-pass designer (orc_remez.c): FIRFilterSpecification.lowPassBuilder()...build() +
+ * FilterFactory.getTaps.  order < 6: estimated (estimateFilterOrder); odd_length -1 unset / 0 / 1.  Returns the number
+ * of taps, -1 if the design does not converge (getTaps returns null), -2 if capacity is too small. */
+int orc_remez_estimate_order(double sampleRate, double frequency1, double frequency2, double passBandRipple,
+                             double stopBandRipple);
+int orc_remez_low_pass(double sampleRate, double passBandEnd, double stopBandStart, double passBandRipple,
+                       double stopBandRipple, int order, int odd_length, int gridDensity, float *out, int capacity);
 
 /* ---------------------------------------------------------------- inverse FFT (a4) */
 typedef struct orc_fft orc_fft;

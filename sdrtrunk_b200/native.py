@@ -82,6 +82,8 @@ PROTOTYPES = {
     "sdrgpu_design_sinc_m2_channelizer": (C.c_int, [C.c_double, C.c_int, C.c_int, _f32p, C.c_int, _i32p]),
     "sdrgpu_design_sinc_m2_synthesizer": (C.c_int, [C.c_double, C.c_double, C.c_int, C.c_int, _f32p, C.c_int, _i32p]),
     "sdrgpu_design_half_band": (C.c_int, [C.c_int, C.c_int, _f32p]),
+    "sdrgpu_design_remez_estimate_order": (C.c_int, [C.c_double] * 5),
+    "sdrgpu_design_remez_low_pass": (C.c_int, [C.c_double] * 5 + [C.c_int, C.c_int, C.c_int, _f32p, C.c_int, _i32p]),
     "sdrgpu_channel_count_for_rate": (C.c_int, [C.c_double]),
     "sdrgpu_channel_indexes": (C.c_int, [C.c_double, C.c_int, C.c_double, C.c_longlong, C.c_int, _i32p, C.c_int, _i32p]),
     "sdrgpu_center_frequency_for_indexes": (C.c_int, [C.c_double, C.c_int, C.c_double, _i32p, C.c_int,

@@ -17,11 +17,13 @@ TOL = 1e-4
 
 
 def c4fm_taps():
-    return ss.remez(72, [0, 5100, 6500, 25000], [1, 0], fs=50000).astype(np.float32)
+    """the taps P25P1DecoderC4FM designs (P25P1DecoderC4FM.java:136-148 through RemezFIRFilterDesigner), 72 taps"""
+    return oracle.c4fm_baseband_taps()
 
 
 def hdqpsk_taps():
-    return ss.remez(154, [0, 6500, 7200, 25000], [1, 0], fs=50000).astype(np.float32)
+    """P25P2DecoderHDQPSK.java:155-166, 154 taps"""
+    return oracle.hdqpsk_baseband_taps()
 
 
 def _noise(rng, c, n, scale=0.3):
@@ -560,7 +562,7 @@ def test_config1_nbfm_chain(gpu):
     carrier = 0.5 * np.exp(1j * (2.5 * np.sin(2 * np.pi * 1000.0 * t) + 2 * np.pi * 100000.0 * t))   # +/-2.5 kHz dev.
     x = sg.interleave(carrier + sg.awgn(rng, n, 1e-3))
     taps = oracle.sinc_m2_channelizer(25000.0, m, 9)
-    fir = ss.remez(45, [0, 5000, 6250, 12500], [1, 0], fs=25000).astype(np.float32)
+    fir = oracle.nbfm_iq_taps()                        # NBFMDecoder.java:306-325, 45 taps
 
     def gpu_chain(demod):
         chan = ComplexPolyphaseChannelizerM2(taps, int(fs), m)

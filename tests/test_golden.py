@@ -54,6 +54,22 @@ def test_oracle_reproduces_filter_fm_chain_golden():
     assert np.array_equal(oracle.convert_samples(c["raw16"].tobytes(), "s16le"), c["s16le"])
 
 
+def test_remez_designers_reproduce_golden_taps():
+    """the decoders' baseband filters as RemezFIRFilterDesigner designs them: oracle and product (csrc/remez.cpp)"""
+    from sdrtrunk_b200.dsp import FilterFactory, FIRFilterSpecification
+    g = load("remez.npz")
+    assert np.array_equal(oracle.c4fm_baseband_taps(), g["c4fm"]) and g["c4fm"].size == 72
+    assert np.array_equal(oracle.hdqpsk_baseband_taps(), g["hdqpsk"]) and g["hdqpsk"].size == 154
+    assert np.array_equal(oracle.nbfm_iq_taps(), g["nbfm"]) and g["nbfm"].size == 45
+    b = FIRFilterSpecification.lowPassBuilder
+    assert np.array_equal(FilterFactory.getTaps(b().sampleRate(50000).passBandCutoff(5100).passBandRipple(0.01).stopBandStart(6500)
+                                                .stopBandRipple(0.01).build()), g["c4fm"])
+    assert np.array_equal(FilterFactory.getTaps(b().sampleRate(50000.0).passBandCutoff(6500).passBandRipple(0.005).stopBandStart(7200)
+                                                .stopBandRipple(0.01).build()), g["hdqpsk"])
+    assert np.array_equal(FilterFactory.getTaps(b().sampleRate(25000.0 * 2).gridDensity(16).oddLength(True).passBandCutoff(10000)
+                                                .passBandRipple(0.01).stopBandStart(12500).stopBandRipple(0.005).build()), g["nbfm"])
+
+
 def test_oracle_reproduces_airspy_and_sync_golden():
     g = load("airspy_sync.npz")
     c = oracle.AirspySampleConverter()

@@ -63,3 +63,74 @@ def test_channel_calculator_known_cases():
     assert c.getCenterFrequencyForIndexes([0, 1]) == 850012500
     with pytest.raises(native.IllegalArgumentException):
         c.getChannelIndexes(TunerChannel(860000000, 12500))               # outside the tuner bandwidth
+
+
+# ---------------------------------------------------------------------------------------------- Remez designer
+DECODER_FILTERS = {
+    # decoder: (sampleRate, passBandCutoff, stopBandStart, passBandRipple, stopBandRipple, oddLength, taps)
+    "c4fm": (50000.0, 5100, 6500, 0.01, 0.01, None, 72),       # P25P1DecoderC4FM.java:136-148
+    "hdqpsk": (50000.0, 6500, 7200, 0.005, 0.01, None, 154),   # P25P2DecoderHDQPSK.java:155-166
+    "nbfm": (50000.0, 10000, 12500, 0.01, 0.005, True, 45),    # NBFMDecoder.java:306-325 (sampleRate = 2 x 25 kHz)
+}
+
+
+def _product_taps(fs, p, s, rp, rs, odd, order=0, density=16):
+    from sdrtrunk_b200.dsp import FilterFactory, FIRFilterSpecification
+    b = (FIRFilterSpecification.lowPassBuilder().sampleRate(fs).passBandCutoff(p).passBandAmplitude(1.0).passBandRipple(rp)
+         .stopBandAmplitude(0.0).stopBandStart(s).stopBandRipple(rs).gridDensity(density))
+    if order:
+        b = b.order(order)
+    if odd is not None:
+        b = b.oddLength(odd)
+    return FilterFactory.getTaps(b.build())
+
+
+@pytest.mark.parametrize("decoder", sorted(DECODER_FILTERS))
+def test_remez_decoder_filters_two_restatements_agree_bit_for_bit(decoder):
+    """RemezFIRFilterDesigner (J/dsp/filter/fir/remez/RemezFIRFilterDesigner.java:52-672) restated twice -- oracle/orc_remez.c
+    statement for statement, sdrtrunk_b200/csrc/remez.cpp on its own structure: the taps the decoders run must agree to
+    the last float bit, have the reference's estimated lengths, and be the equiripple low-pass the specification asks for."""
+    import scipy.signal as ss
+    fs, p, s, rp, rs, odd, n = DECODER_FILTERS[decoder]
+    want = oracle.remez_low_pass(fs, p, s, rp, rs, odd_length=odd)
+    got = _product_taps(fs, p, s, rp, rs, odd)
+    assert want is not None and got is not None
+    assert got.size == n == want.size
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    assert np.array_equal(got, got[::-1])                               # linear phase
+    w, h = ss.freqz(got.astype(np.float64), worN=8192, fs=fs)
+    mag = np.abs(h)
+    assert np.max(np.abs(mag[w <= p] - 1.0)) < 0.05 and np.max(mag[w >= s]) < 0.012     # ~ -40 dB stop band
+    # equiripple: the stop-band error touches its bound at (nearly) every lobe
+    lobes = mag[w >= s]
+    peaks = lobes[1:-1][(lobes[1:-1] > lobes[:-2]) & (lobes[1:-1] > lobes[2:])]
+    assert peaks.size > 5 and np.min(peaks) > 0.7 * np.max(peaks)
+    # same design problem as the textbook algorithm: close to scipy's remez with the specification's weights
+    rip = lambda db: (10 ** (db / 20) - 1) / (10 ** (db / 20) + 1)
+    ref = ss.remez(n, [0, p, s, fs / 2], [1, 0], weight=[1 / rip(rp), 1 / rip(rs)], fs=fs)
+    assert np.max(np.abs(got - ref)) < 1e-2                              # (the Java resamples its polynomial on a slightly different grid than it inverts on)
+
+
+def test_remez_order_estimate_and_other_specifications():
+    from sdrtrunk_b200.dsp import FIRFilterSpecification
+    for args in ((50000.0, 5100, 6500, 0.01, 0.01), (50000.0, 6500, 7200, 0.005, 0.01), (50000.0, 10000, 12500, 0.01, 0.005),
+                 (25000.0, 3000, 4000, 0.1, 0.02), (48000.0, 3000, 3400, 0.02, 0.001)):
+        assert FIRFilterSpecification.estimateFilterOrder(*args) == oracle.remez_estimate_order(*args)
+    assert FIRFilterSpecification.estimateFilterOrder(50000.0, 5100, 6500, 0.01, 0.01) == 71
+    rng = np.random.default_rng(12)
+    agreed = 0
+    for _ in range(12):                                                 # random specifications, explicit orders, both parities
+        fs = float(rng.choice([8000, 25000, 48000, 50000]))
+        p = float(rng.uniform(0.05, 0.3) * fs)
+        s = p + float(rng.uniform(0.03, 0.1) * fs)
+        rp, rs = float(rng.uniform(0.005, 0.1)), float(rng.uniform(0.002, 0.05))
+        order = int(rng.integers(20, 90))
+        odd = [None, True, False][int(rng.integers(0, 3))]
+        density = int(rng.choice([8, 16]))
+        want = oracle.remez_low_pass(fs, p, s, rp, rs, order=order, odd_length=odd, grid_density=density)
+        got = _product_taps(fs, p, s, rp, rs, odd, order, density)
+        assert (want is None) == (got is None)                          # both fail to converge, or neither
+        if want is not None:
+            assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+            agreed += 1
+    assert agreed >= 6

@@ -88,13 +88,13 @@ def test_p25_chains_decode_synthetic_signal(kind):
     n = int(dib.size * 50000 / rate) // 2048 * 2048
     if kind == "c4fm":
         x = sg.c4fm(dib, carrier_offset=150.0, timing_phase=0.4, n_samples=n)
-        chain = oracle.P25Chain(oracle.C4FM, 50000.0, ss.remez(72, [0, 5100, 6500, 25000], [1, 0], fs=50000))
+        chain = oracle.P25Chain(oracle.C4FM, 50000.0, oracle.c4fm_baseband_taps())
     elif kind == "lsm":
         x = sg.dqpsk(dib, symbol_rate=rate, carrier_offset=-90.0, timing_phase=0.3, n_samples=n)
         chain = oracle.P25Chain(oracle.LSM, 50000.0)
     else:
         x = sg.dqpsk(dib, symbol_rate=rate, carrier_offset=60.0, timing_phase=0.7, n_samples=n)
-        chain = oracle.P25Chain(oracle.HDQPSK, 50000.0, ss.remez(154, [0, 6500, 7200, 25000], [1, 0], fs=50000))
+        chain = oracle.P25Chain(oracle.HDQPSK, 50000.0, oracle.hdqpsk_baseband_taps())
     x = x + sg.awgn(rng, n, 0.02)
     decoded = chain.receive(sg.interleave(x))
     assert abs(decoded.size - n * rate / 50000) < 6
@@ -151,7 +151,7 @@ def test_half_band_streaming_and_cascade():
 
 def test_fir_matches_lfilter():
     rng = np.random.default_rng(4)
-    taps = ss.remez(45, [0, 5000, 6250, 12500], [1, 0], fs=25000).astype(np.float32)
+    taps = oracle.nbfm_iq_taps()
     x = rng.standard_normal(2 * 3000).astype(np.float32)
     got = sg.deinterleave(oracle.ComplexFIR(taps).filter(x))
     want = ss.lfilter(taps.astype(np.float64), 1.0, sg.deinterleave(x))
@@ -271,7 +271,7 @@ def test_inversion_feedback_recovers_a_falsely_locked_loop(offset, event):
     dibits come out rotated until the rotated sync pattern is seen and correctInversion is applied; from then on the
     normal pattern is found and the payload decodes (P25P1SyncDetector.java:122-130)."""
     import scipy.signal as ss
-    taps = ss.remez(72, [0, 5100, 6500, 25000], [1, 0], fs=50000).astype(np.float32)
+    taps = oracle.c4fm_baseband_taps()
     rng = np.random.default_rng(11)
     d = sg.dibits_with_sync(rng, 2000, sg.P25_PHASE1_SYNC, 48)
     n = 20 * 1024

@@ -6,7 +6,6 @@ import os
 import sys
 
 import numpy as np
-import scipy.signal as ss
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -38,7 +37,7 @@ def main():
                         synth=synth)
     # ---- filters: half-band cascade x8, 72-tap FIR, AGC
     xf = (0.3 * rng.standard_normal(2 * 2048)).astype(np.float32)
-    fir = ss.remez(72, [0, 5100, 6500, 25000], [1, 0], fs=50000).astype(np.float32)
+    fir = oracle.c4fm_baseband_taps()
     np.savez_compressed(os.path.join(OUT, "filters.npz"), x=xf, fir=fir, decimate8=oracle.Decimator(8).decimate_complex(xf),
                         fir72=oracle.ComplexFIR(fir).filter(xf), agc=np.concatenate([oracle.agc_block(xf[:2048]),
                                                                                      oracle.agc_block(xf[2048:])]))
@@ -57,7 +56,7 @@ def main():
             t = fir
         else:
             zz = sg.dqpsk(dib, symbol_rate=rate, carrier_offset=-80.0, timing_phase=0.61, n_samples=nn)
-            t = None if kind == "lsm" else ss.remez(154, [0, 6500, 7200, 25000], [1, 0], fs=50000).astype(np.float32)
+            t = None if kind == "lsm" else oracle.hdqpsk_baseband_taps()
         xx = sg.interleave(zz + sg.awgn(rng, nn, 0.03))
         d, agc = oracle.P25Chain(okind, 50000.0, t).receive(xx, want_agc=True)
         out[kind + "_x"] = xx
@@ -85,6 +84,9 @@ def main():
     chain.attach_sync(oracle.SYNC_P25_PHASE1, 50000.0)
     np.savez_compressed(os.path.join(OUT, "airspy_sync.npz"), raw_unpacked=raw_u, raw_packed=raw_p, iq=iq, sync_x=xs, sync_fir=fir,
                         sync_symbols=chain.receive(xs))
+    # ---- the decoders' Remez-designed baseband filters (oracle/orc_remez.c; csrc/remez.cpp must reproduce them bit for bit)
+    np.savez_compressed(os.path.join(OUT, "remez.npz"), c4fm=oracle.c4fm_baseband_taps(), hdqpsk=oracle.hdqpsk_baseband_taps(),
+                        nbfm=oracle.nbfm_iq_taps())
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -17,12 +17,19 @@ from sdrtrunk_b200 import native  # noqa: E402
 from sdrtrunk_b200.dsp import Bank, ComplexPolyphaseChannelizerM2, Pipeline  # noqa: E402
 
 
+def oracle_taps():
+    """the C4FM decoder's own baseband filter (libsdrgpu's restatement of RemezFIRFilterDesigner)"""
+    from sdrtrunk_b200.dsp import FilterFactory, FIRFilterSpecification
+    return FilterFactory.getTaps(FIRFilterSpecification.lowPassBuilder().sampleRate(50000.0).passBandCutoff(5100)
+                                 .passBandRipple(0.01).stopBandStart(6500).stopBandRipple(0.01).build())
+
+
 def main():
     native.init(0)
     L = native.lib()
     m, fs = 400, 10e6
     n = 48 * 1024 * (m // 2)
-    fir = ss.remez(72, [0, 5100, 6500, 25000], [1, 0], fs=50000).astype(np.float32)
+    fir = oracle_taps()
     x_dev = torch.randn(2 * n, device="cuda", dtype=torch.float32) * 0.01
     x_host = torch.empty(2 * n, dtype=torch.float32, pin_memory=True)
     x_host.copy_(x_dev)

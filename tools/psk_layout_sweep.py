@@ -15,11 +15,18 @@ from sdrtrunk_b200 import native  # noqa: E402
 from sdrtrunk_b200.dsp import Bank  # noqa: E402
 
 
+def oracle_taps():
+    """the C4FM decoder's own baseband filter (libsdrgpu's restatement of RemezFIRFilterDesigner)"""
+    from sdrtrunk_b200.dsp import FilterFactory, FIRFilterSpecification
+    return FilterFactory.getTaps(FIRFilterSpecification.lowPassBuilder().sampleRate(50000.0).passBandCutoff(5100)
+                                 .passBandRipple(0.01).stopBandStart(6500).stopBandRipple(0.01).build())
+
+
 def main():
     native.init(0)
     rng = np.random.default_rng(0)
     n = 24 * 1024
-    fir = ss.remez(72, [0, 5100, 6500, 25000], [1, 0], fs=50000).astype(np.float32)
+    fir = oracle_taps()
     base = []
     for k in range(8):
         dib = rng.integers(0, 4, int(n * 4800 / 50000) + 8)

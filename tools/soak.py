@@ -23,7 +23,7 @@ def main(seconds):
     rng = np.random.default_rng(0)
     m, fs = 96, 2.4e6
     taps = FilterFactory.getSincM2Channelizer(25000.0, m, 9)
-    fir = ss.remez(72, [0, 5100, 6500, 25000], [1, 0], fs=50000).astype(np.float32)
+    fir = oracle_taps()
     n_ch = 8 * 1024
     bins = [3, 17, 40, 60]
     base = [sg.c4fm(sg.dibits_with_sync(rng, n_ch // 10 + 8, sg.P25_PHASE1_SYNC, 48), carrier_offset=off, n_samples=n_ch,
