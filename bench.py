@@ -490,7 +490,7 @@ class TunerInputs:
 class TunerWorkload:
     """T tuner streams of one GPU: T channelizers (+ one bank over all their channels + the multi-tuner pipeline)."""
 
-    def __init__(self, name, inputs, tuners, local_rank):
+    def __init__(self, name, inputs, tuners, local_rank, bins=None):
         import torch
         from sdrtrunk_b200 import native
         from sdrtrunk_b200.dsp import Bank, ComplexPolyphaseChannelizerM2, Pipeline
@@ -507,15 +507,20 @@ class TunerWorkload:
         self.truth = inputs.truth[:tuners]
         self.stream = torch.cuda.Stream(device=dev)
         self.chans = []
+        # level 2 of SURVEY.md 8e: this rank keeps (and demodulates) the polyphase bins [lo, hi) of every tuner
+        self.bins = bins if bins is not None else (0, m)
+        self.rows_per_tuner = self.bins[1] - self.bins[0]
         for _ in range(tuners):
             ch = ComplexPolyphaseChannelizerM2(fs, cfg["taps_per_channel"], device=local_rank, maxInputFloats=self.n_floats)
+            if bins is not None:
+                ch.setChannels(list(range(*bins)))
             ch.setStream(self.stream.cuda_stream)
             self.chans.append(ch)
         self.pipeline = None
         self._host = {}
         self.fmt = "f32"
         if cfg["demod"]:
-            rows = tuners * m
+            rows = tuners * self.rows_per_tuner
             self.bank = Bank.preset(native.PRESET_P25_C4FM, rows, 2 * fs / m, fir_taps("c4fm"),
                                     max_samples_per_call=self.n_blocks, device=local_rank)
             self.bank.setStream(self.stream.cuda_stream)
@@ -601,12 +606,13 @@ class TunerWorkload:
         self.step_host()
         cnt = self.cnt_host.numpy()
         out = {}
-        rows = self.T * self.m
-        for r in sorted({0, 57, self.m // 2, self.m - 1, rows - self.m + 3, rows - 1}):
-            t, c = divmod(r, self.m)
+        per = self.rows_per_tuner
+        rows = self.T * per
+        for r in sorted({0, min(57, per - 1), per // 2, per - 1, rows - per + min(3, per - 1), rows - 1}):
+            t, c = divmod(r, per)
             dec = self.sym_host.numpy()[r, :cnt[r]]
-            out["tuner%d_bin%d" % (t, c)] = {"symbols": int(cnt[r]),
-                                             "match_after_acquisition": round(dibit_match(dec, self.truth[t][c]), 4)}
+            out["tuner%d_bin%d" % (t, self.bins[0] + c)] = {
+                "symbols": int(cnt[r]), "match_after_acquisition": round(dibit_match(dec, self.truth[t][self.bins[0] + c]), 4)}
         if self.T > 1 or self.n_floats > 50000000:
             self._host.pop("f32", None)        # hundreds of MB of pinned memory per tuner: only kept for T = 1
         return out
@@ -920,6 +926,54 @@ def run_bank(name, args, rank, world, local_rank, torch, dist, as_secondary=Fals
     return line
 
 
+def run_level2(args, rank, world, local_rank, torch, dist, timed, peak, peak_src):
+    """SURVEY.md 8e level 2: ONE set of tuner streams on several GPUs.  Every rank receives the same tuner buffers, runs
+    the (cheap) filter bank + inverse DFT, and keeps only its contiguous slice of the polyphase bins, which it filters and
+    demodulates.  No collective on the data path; strong scaling (the job is fixed, value = its input rate)."""
+    import zlib
+    from sdrtrunk_b200 import sharding
+    dev = torch.device("cuda", local_rank)
+    cfg = WORKLOADS[args.workload]
+    inputs = TunerInputs(torch, dev, args.workload, 0, args.tuners)       # rank-independent seeds: the same streams everywhere
+    lo, hi = sharding.bin_slice(inputs.m, rank, world)
+    w = TunerWorkload(args.workload, inputs, args.tuners, local_rank, bins=(lo, hi))
+    sanity = w.sanity()
+    cnt = w.cnt_host.numpy().copy()
+    digest = {(t, lo + c): zlib.crc32(w.sym_host.numpy()[t * (hi - lo) + c, :cnt[t * (hi - lo) + c]].tobytes())
+              for t in range(args.tuners) for c in range(hi - lo)}
+    w.set_format("f32")
+    ms, _ = timed(w.step_device, w.stream, args.steps, args.warmup)
+    gathered = [digest]
+    if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, digest)
+    w.dispose()
+    check = None
+    if rank == 0 and args.verify:
+        # the unsharded run of the same streams on this GPU: every channel's dibits must be the ones the slices produced
+        full = TunerWorkload(args.workload, inputs, args.tuners, local_rank)
+        full.sanity()
+        fc = full.cnt_host.numpy()
+        want = {(t, c): zlib.crc32(full.sym_host.numpy()[t * full.m + c, :fc[t * full.m + c]].tobytes())
+                for t in range(args.tuners) for c in range(full.m)}
+        got = {}
+        for g in gathered:
+            got.update(g)
+        check = {"channels": len(want), "identical_to_unsharded": got == want}
+        full.dispose()
+    if rank != 0:
+        return
+    total = args.tuners * inputs.n_complex
+    line = {"metric": METRIC, "value": total / (ms / args.steps * 1e-3) / 1e6, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": dict(workload_config(args.workload, args.tuners),
+                           sharding="level 2: every GPU channelizes the same tuner streams and demodulates M / N of the bins, "
+                                    "no collective"),
+            "bins_of_rank0": [lo, hi], "verify": check, "decode_sanity": sanity}
+    print(json.dumps(line))
+
+
 def run_gpu(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -948,6 +1002,11 @@ def run_gpu(args, rank, world, local_rank):
 
     chain = cfg["demod"] is not None
     tuners = args.tuners if chain else 1
+    if args.sharding == "level2":
+        run_level2(args, rank, world, local_rank, torch, dist, timed, peak, peak_src)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     extras = (not args.no_extra) and world == 1 and args.workload == "c4fm_20m"
     curve_counts = [t for t in (1, 2, 4, 8) if t != tuners] if extras else []
     inputs = TunerInputs(torch, dev, args.workload, rank, max([tuners] + curve_counts))
@@ -1040,6 +1099,10 @@ def main():
     ap.add_argument("--workload", default="c4fm_20m", choices=sorted(WORKLOADS))
     ap.add_argument("--tuners", type=int, default=int(os.environ.get("SDRGPU_BENCH_TUNERS", DEFAULT_TUNERS)),
                     help="tuner streams per GPU batched into one bank (chain workloads)")
+    ap.add_argument("--sharding", default="level1", choices=["level1", "level2"],
+                    help="level1: independent tuner streams per GPU (weak scaling); level2: the same streams on every GPU, each "
+                         "keeping a slice of the polyphase bins (strong scaling)")
+    ap.add_argument("--verify", action="store_true", help="level2: compare every channel's dibits with the unsharded run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary measurements (tuner-count curve, other configs)")
     ap.add_argument("--device-only", action="store_true",

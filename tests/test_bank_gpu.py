@@ -926,3 +926,29 @@ def test_config5_shape_800_channels_pipeline(gpu):
         assert np.array_equal(got[k], want), k
         y = oracle.OneChannelOutputProcessor(50000.0, k, float(m)).process(res)
         assert sg.rel_rms(iq[k][:2 * head], y) < TOL, k
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_level2_bin_slices_equal_the_unsharded_pipeline(gpu, world):
+    """SURVEY.md 8e level 2 on the device: every "rank" channelizes the same tuner buffer and keeps its slice of the bins
+    (sharding.bin_slice); the slices' dibits, put together, are those of the unsharded run -- all M = 96 bins busy."""
+    from sdrtrunk_b200 import sharding
+    from sdrtrunk_b200.dsp import Bank, ComplexPolyphaseChannelizerM2, Pipeline
+    m, n_ch = 96, 4 * 1024
+    rng = np.random.default_rng(81)
+    x = _tuner_stream(rng, m, n_ch, list(range(m)))
+    taps, fir = oracle.sinc_m2_channelizer(25000.0, m, 9), c4fm_taps()
+
+    def run(lo, hi):
+        chan = ComplexPolyphaseChannelizerM2(taps, 2400000, m, maxInputFloats=x.size)
+        if (lo, hi) != (0, m):
+            chan.setChannels(list(range(lo, hi)))
+        return Pipeline(chan, Bank.preset(gpu.PRESET_P25_C4FM, hi - lo, 50000.0, fir, max_samples_per_call=n_ch)).process(x)
+
+    want = run(0, m)
+    got = []
+    for rank in range(world):
+        got += run(*sharding.bin_slice(m, rank, world))
+    assert len(got) == m
+    for k in range(m):
+        assert np.array_equal(got[k], want[k]), k

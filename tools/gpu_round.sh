@@ -1,6 +1,6 @@
 #!/bin/bash
-# One GPU-box round: parity tests, smoke, bench (both arms), then the ncu launch list and the full capture of the
-# dominant kernels.  Run as:  gpurun --timeout 1500 -- 'bash tools/gpu_round.sh r01'
+# One GPU-box round: parity tests, smoke, bench (both arms), compute-sanitizer on the smoke path, then the ncu launch
+# list and the full capture of the dominant kernels.  Run as:  gpurun --timeout 1800 -- 'bash tools/gpu_round.sh r02'
 # ncu only runs after the identical plain command exited 0 (B200_PROFILING.md).
 tag=${1:-rXX}
 out=gpurun_out
@@ -11,14 +11,24 @@ tail -3 $out/${tag}_pytest.log
 python __graft_entry__.py smoke > $out/${tag}_smoke.log 2>&1; echo "smoke rc=$?" | tee -a $out/${tag}_smoke.log
 tail -2 $out/${tag}_smoke.log
 python bench.py > $out/${tag}_bench.json 2> $out/${tag}_bench.err; echo "bench rc=$?"
-cat $out/${tag}_bench.json
+head -c 1500 $out/${tag}_bench.json; echo
 python bench.py --impl reference --steps 3 --warmup 1 > $out/${tag}_bench_reference.json 2> $out/${tag}_bench_reference.err
-cat $out/${tag}_bench_reference.json
+head -c 600 $out/${tag}_bench_reference.json; echo
+if [ "$2" != "nosan" ]; then
+# memory and shared-memory race checks of the smoke path (channelizer + C4FM chain) and of the fused NBFM / multi-tuner paths
+compute-sanitizer --tool memcheck --error-exitcode 1 python __graft_entry__.py smoke > $out/${tag}_memcheck.log 2>&1; echo "memcheck rc=$?" | tee -a $out/${tag}_memcheck.log
+compute-sanitizer --tool racecheck --error-exitcode 1 python __graft_entry__.py smoke > $out/${tag}_racecheck.log 2>&1; echo "racecheck rc=$?" | tee -a $out/${tag}_racecheck.log
+compute-sanitizer --tool memcheck --error-exitcode 1 python -m pytest tests/test_bank_gpu.py -m gpu -x -q -k "config1_nbfm or squelching or multi_tuner_pipeline_equals or dibits_bit_exact" > $out/${tag}_memcheck_tests.log 2>&1; echo "memcheck tests rc=$?" | tee -a $out/${tag}_memcheck_tests.log
+tail -3 $out/${tag}_memcheck.log $out/${tag}_racecheck.log $out/${tag}_memcheck_tests.log
+fi
 if [ "$2" != "noncu" ]; then
-CMD="python bench.py --workload c4fm --steps 1 --warmup 3 --no-cpu-baseline --device-only"
+CMD="python bench.py --steps 2 --warmup 3 --no-extra --no-cpu-baseline --device-only"
 $CMD > $out/${tag}_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/${tag}_launches.csv $CMD > $out/${tag}_ncu1.log 2>&1
 $CMD > $out/${tag}_plain2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:'pfb|fir|psk' -s 9 -c 3 -o $out/${tag}_prof $CMD > $out/${tag}_ncu2.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'pfb2|fir_agc|psk' -s 30 -c 12 -o $out/${tag}_prof $CMD > $out/${tag}_ncu2.log 2>&1
 tail -5 $out/${tag}_ncu2.log
+CMD2="python bench.py --workload nbfm_4096 --steps 1 --warmup 3 --no-cpu-baseline --device-only"
+$CMD2 > $out/${tag}_plain3.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:'nbfm' -s 3 -c 1 -o $out/${tag}_prof_nbfm $CMD2 > $out/${tag}_ncu3.log 2>&1
 fi
