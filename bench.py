@@ -411,7 +411,7 @@ def synth_dqpsk_channels(torch, dev, n_channels, n, seed, symbol_rate=6000.0, fs
     return out, truth.numpy()
 
 
-def synth_nbfm_channels(torch, dev, n_channels, n, seed, fs=50000.0, noise=1e-3):
+def synth_nbfm_channels(torch, dev, n_channels, n, seed, fs=50000.0, noise=3e-5):
     """configs[0] as a bank: channel-domain NBFM carriers at 50 kHz (audio tone 300-3000 Hz, +/-2.5 kHz deviation,
     amplitude 0.5, carrier offset U(-500, 500) Hz) + AWGN; every 8th channel carries noise only (stays squelched)."""
     g = torch.Generator(device=dev)
