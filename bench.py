@@ -35,7 +35,7 @@ sys.path.insert(0, ROOT)
 METRIC = "channelized+demodulated complex MS/s and real-time channel count at 1/2/4/8 GPU"
 UNIT = "MS/s"
 FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12   # FFMA lanes x 2 flop x max SM clock
-DEFAULT_TUNERS = 4                                   # tuner streams per GPU of the headline workload
+DEFAULT_TUNERS = 8                                   # tuner streams per GPU of the headline workload (all of configs[4])
 
 WORKLOADS = {
     # BASELINE.json configs[4]: 20 MS/s tuners -> 800 channels each, full chain (the headline)
