@@ -1,5 +1,5 @@
 #!/bin/bash
-# One GPU-box round: parity tests, smoke, bench (both arms), compute-sanitizer on the smoke path, then the ncu launch
+# One GPU-box round: parity tests, smoke, bench (both arms), then the ncu launch
 # list and the full capture of the dominant kernels.  Run as:  gpurun --timeout 1800 -- 'bash tools/gpu_round.sh r02'
 # ncu only runs after the identical plain command exited 0 (B200_PROFILING.md).
 tag=${1:-rXX}
@@ -14,13 +14,9 @@ python bench.py > $out/${tag}_bench.json 2> $out/${tag}_bench.err; echo "bench r
 head -c 1500 $out/${tag}_bench.json; echo
 python bench.py --impl reference --steps 3 --warmup 1 > $out/${tag}_bench_reference.json 2> $out/${tag}_bench_reference.err
 head -c 600 $out/${tag}_bench_reference.json; echo
-if [ "$2" != "nosan" ]; then
-# memory and shared-memory race checks of the smoke path (channelizer + C4FM chain) and of the fused NBFM / multi-tuner paths
-compute-sanitizer --tool memcheck --error-exitcode 1 python __graft_entry__.py smoke > $out/${tag}_memcheck.log 2>&1; echo "memcheck rc=$?" | tee -a $out/${tag}_memcheck.log
-compute-sanitizer --tool racecheck --error-exitcode 1 python __graft_entry__.py smoke > $out/${tag}_racecheck.log 2>&1; echo "racecheck rc=$?" | tee -a $out/${tag}_racecheck.log
-compute-sanitizer --tool memcheck --error-exitcode 1 python -m pytest tests/test_bank_gpu.py -m gpu -x -q -k "config1_nbfm or squelching or multi_tuner_pipeline_equals or dibits_bit_exact" > $out/${tag}_memcheck_tests.log 2>&1; echo "memcheck tests rc=$?" | tee -a $out/${tag}_memcheck_tests.log
-tail -3 $out/${tag}_memcheck.log $out/${tag}_racecheck.log $out/${tag}_memcheck_tests.log
-fi
+# (compute-sanitizer memcheck / racecheck of the smoke path were part of this round until the pool closed the tool:
+#  "compute-sanitizer is closed on this pool and stays closed: runs under it have left GPUs needing a reset" -- r2j_memcheck.log.
+#  Bounds are covered by the parity tests instead: ragged / oversized / empty calls, odd channel counts, partial tiles.)
 if [ "$2" != "noncu" ]; then
 CMD="python bench.py --steps 2 --warmup 3 --no-extra --no-cpu-baseline --device-only"
 $CMD > $out/${tag}_plain.log 2>&1 &&
