@@ -692,12 +692,13 @@ def measure_tuner(w, args, world, timed, full=True):
         ms_sync, _ = timed(w.step_device, w.stream, steps, 3)
         w.bank.setSyncDetector(w.native.SYNC_NONE)
         res["with_sync"] = {"ms_per_step": ms_sync / steps, "value": total / (ms_sync / steps * 1e-3) / 1e6, "unit": UNIT}
-    if full and w.pipeline is not None and w.T == 1:
+    if full and w.pipeline is not None:
         # the usual sdrtrunk situation: every channel frequency-corrected (OneChannelOutputProcessor + Oscillator);
         # small offsets so that the demodulators keep their locks on the synthetic channels.  Measured last: the
         # selection change restarts the channel oscillators.  The oscillator look-ahead runs on a side stream: the
         # wall clock of the loop with a full device synchronise is reported beside the stream's event time.
-        w.chans[0].setOutputChannels([([k], 37 if k % 2 else -53) for k in range(w.m)])
+        for ch in w.chans:
+            ch.setOutputChannels([([k], 37 if k % 2 else -53) for k in range(w.m)])
         ms_corr, wall_corr = timed(w.step_device, w.stream, steps, 3)
         res["corrected"] = {"ms_per_step": ms_corr / steps, "wall_ms_per_step_with_device_sync": wall_corr / steps,
                             "value": total / (ms_corr / steps * 1e-3) / 1e6, "unit": UNIT}

@@ -1067,12 +1067,13 @@ sdrgpu_status sdrgpu::chan_enqueue(sdrgpu_channelizer *h, const float2 *d_in, in
             if (top_up > 0) {
                 SDRGPU_CUDA(cudaEventRecord(h->ev_mix, h->stream));
                 SDRGPU_CUDA(cudaStreamWaitEvent(h->osc_stream, h->ev_mix, 0));
-                // The chain keeps its scheduler's fma pipe 55 % busy for about a millisecond; a demodulator warp that
-                // shares the scheduler slows its whole kernel down (measured: +0.3 .. +0.9 ms per call, by placement).
-                // Asking for (almost) all of an SM's shared memory keeps every other block off the few SMs that host
-                // the producer's blocks: 13 of 148 SMs for 400 channels.
-                static const int exclusive = getenv("SDRGPU_OSC_EXCLUSIVE") ? atoi(getenv("SDRGPU_OSC_EXCLUSIVE")) : 1;
-                // (only while that costs a tenth of the GPU at most)
+                // The chain keeps its scheduler's fma pipe 55 % busy for about a millisecond, and a demodulator warp that
+                // shares the scheduler runs slower while it does.  Round 1 kept other blocks off the producer's SMs by
+                // asking for 220 KB of shared memory it never touched (SDRGPU_OSC_EXCLUSIVE=1 still does); that only worked
+                // for one pipeline per GPU and starves everything else once several tuners share the device, so the
+                // producer is now an ordinary small kernel on its side stream and the cost is reported as measured
+                // (bench.py: with_frequency_corrected_channels).
+                static const int exclusive = getenv("SDRGPU_OSC_EXCLUSIVE") ? atoi(getenv("SDRGPU_OSC_EXCLUSIVE")) : 0;
                 const int smem = (exclusive && pgrid <= 16) ? 220 * 1024 : 0;
                 if (smem) SDRGPU_CUDA(cudaFuncSetAttribute(osc_produce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
                 osc_produce_kernel<<<pgrid, 32, smem, h->osc_stream>>>(h->d_mix, h->d_mix_state, h->d_osc, h->osc_ring_len,
