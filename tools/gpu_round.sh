@@ -20,7 +20,7 @@ head -c 600 $out/${tag}_bench_reference.json; echo
 if [ "$2" != "noncu" ]; then
 CMD="python bench.py --steps 2 --warmup 3 --no-extra --no-cpu-baseline --device-only"
 $CMD > $out/${tag}_plain.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/${tag}_launches.csv $CMD > $out/${tag}_ncu1.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'pfb|fir_agc|psk|carry|append|convert|osc|halfband|fm_|nbfm|save_state' -c 1200 --csv --log-file $out/${tag}_launches.csv $CMD > $out/${tag}_ncu1.log 2>&1
 $CMD > $out/${tag}_plain2.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:'pfb2|fir_agc|psk' -s 30 -c 12 -o $out/${tag}_prof $CMD > $out/${tag}_ncu2.log 2>&1
 tail -5 $out/${tag}_ncu2.log
