@@ -53,6 +53,14 @@ sdrgpu_status sdrgpu_memcpy(void *dst, const void *src, size_t bytes, int dst_me
 sdrgpu_status sdrgpu_device_synchronize(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 uint64_t sdrgpu_launch_count(void);
+/* Process-wide tuning knobs (launch shapes only: results never depend on them).  Unknown knob -> INVALID_ARG.
+ *   FIR_CTAS_PER_SM / PFB_CTAS_PER_SM: resident CTAs per SM of fir_agc_kernel / pfb2_kernel while a pipeline runs its
+ *   time chunks concurrently with the symbol demodulator (0 = whatever fits).  The demodulator is bound by the latency of
+ *   its per-symbol feedback chain; every other resident warp on its scheduler delays each of its dependent instructions,
+ *   so the filter kernels that overlap it are held to a few warps per scheduler. */
+enum { SDRGPU_TUNE_FIR_CTAS_PER_SM = 0, SDRGPU_TUNE_PFB_CTAS_PER_SM = 1, SDRGPU_TUNE_THROTTLE_ALWAYS = 2, SDRGPU_TUNE_COUNT = 8 };
+sdrgpu_status sdrgpu_set_tuning(int knob, int value);
+int sdrgpu_get_tuning(int knob);
 
 /* ------------------------------------------------------------------ filter design (host side, runs once)
  * J/dsp/filter/FilterFactory.java:755-770 (getSincM2Synthesizer), :808-920 (getSincM2Channelizer),

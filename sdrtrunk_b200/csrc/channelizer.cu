@@ -761,6 +761,7 @@ struct sdrgpu_channelizer {
     int M = 0, T = 0, half = 0, H = 0, NB = 16;
     int max_in_complex = 0, max_blocks = 0;
     int leftover = 0, parity0 = 0;
+    bool throttled = false;   // chan_set_throttled: the pipeline is overlapping this launch with the demodulator
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaStream_t copy_in = nullptr, copy_out = nullptr;   // H2D / D2H streams of the chunked host path
     cudaEvent_t events[kMaxEvents] = {};
@@ -928,9 +929,11 @@ sdrgpu_status launch_pfb2(const sdrgpu_channelizer *h, const ChanParams &p)
 {
     using L = Pfb2Layout<M, R1, R2, NB, TT, NT>;
     auto kernel = pfb2_kernel<M, R1, R2, NB, TT, NT, MINB>;
-    SDRGPU_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::smem_bytes));
+    // a pipeline that overlaps its time chunks with the demodulator holds the channelizer to a few CTAs per SM
+    const size_t smem = (h->throttled || g_tuning[SDRGPU_TUNE_THROTTLE_ALWAYS]) ? smem_for_ctas_per_sm(L::smem_bytes, 0, g_tuning[SDRGPU_TUNE_PFB_CTAS_PER_SM]) : L::smem_bytes;
+    SDRGPU_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > L::smem_bytes ? 227 * 1024 : L::smem_bytes)));
     const int grid = (p.n_blocks + NB - 1) / NB;
-    kernel<<<grid, NT, L::smem_bytes, h->stream>>>(p);
+    kernel<<<grid, NT, smem, h->stream>>>(p);
     count_launch();
     SDRGPU_CUDA(cudaGetLastError());
     return SDRGPU_OK;
@@ -1152,6 +1155,7 @@ const float2 *sdrgpu::chan_convert(sdrgpu_channelizer *h, const void *iq_device,
     }
     return h->d_in + first;
 }
+void sdrgpu::chan_set_throttled(sdrgpu_channelizer *h, bool on) { h->throttled = on; }
 int sdrgpu::chan_half(const sdrgpu_channelizer *h) { return h->half; }
 int sdrgpu::chan_max_in(const sdrgpu_channelizer *h) { return h->max_in_complex; }
 int sdrgpu::chan_leftover(const sdrgpu_channelizer *h) { return h->leftover; }

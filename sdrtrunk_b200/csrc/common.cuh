@@ -13,6 +13,19 @@ namespace sdrgpu {
 
 extern thread_local std::string g_last_error;
 extern std::atomic<uint64_t> g_launches;
+extern int g_tuning[SDRGPU_TUNE_COUNT];   // sdrgpu_set_tuning
+
+// dynamic shared memory a launch has to ask for so that at most `ctas` CTAs of it fit on one SM (228 KB per SM, 1 KB
+// reserved per CTA); never less than `need`.  0 CTAs = no limit.
+inline size_t smem_for_ctas_per_sm(size_t need, size_t static_bytes, int ctas)
+{
+    if (ctas <= 0) return need;
+    const size_t per = (228 * 1024) / (size_t)(ctas + 1) + 1024;   // one more CTA of this size no longer fits
+    const size_t want = per > static_bytes + 1024 ? per - static_bytes - 1024 : 0;
+    const size_t cap = 227 * 1024 - static_bytes;
+    const size_t v = want > need ? want : need;
+    return v > cap ? cap : v;
+}
 
 inline sdrgpu_status fail(sdrgpu_status code, const char *fmt, ...)
 {
@@ -52,6 +65,7 @@ sdrgpu_status chan_upload(sdrgpu_channelizer *h, const void *iq, size_t first, i
 const float2 *chan_convert(sdrgpu_channelizer *h, const void *iq_device_or_null, size_t first, int n);
 size_t chan_complex_bytes(const sdrgpu_channelizer *h);   // bytes of one complex sample in the handle's input format
 int chan_half(const sdrgpu_channelizer *h);
+void chan_set_throttled(sdrgpu_channelizer *h, bool on);   // next launches share the GPU with the demodulator (SDRGPU_TUNE_PFB_CTAS_PER_SM)
 int chan_max_in(const sdrgpu_channelizer *h);
 int chan_leftover(const sdrgpu_channelizer *h);  // samples buffered that did not fill a block yet (mSampleBufferPointer)   // complex samples one process call may carry (max_input_floats / 2)
 

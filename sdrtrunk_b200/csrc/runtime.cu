@@ -4,6 +4,7 @@
 namespace sdrgpu {
 thread_local std::string g_last_error;
 std::atomic<uint64_t> g_launches{0};
+int g_tuning[SDRGPU_TUNE_COUNT] = {0};
 }  // namespace sdrgpu
 
 using namespace sdrgpu;
@@ -13,6 +14,15 @@ extern "C" {
 const char *sdrgpu_last_error(void) { return g_last_error.c_str(); }
 const char *sdrgpu_version(void) { return "sdrgpu 0.1 (sm_100a)"; }
 uint64_t sdrgpu_launch_count(void) { return g_launches.load(); }
+
+sdrgpu_status sdrgpu_set_tuning(int knob, int value)
+{
+    if (knob < 0 || knob >= SDRGPU_TUNE_COUNT) return fail(SDRGPU_ERR_INVALID_ARG, "unknown tuning knob %d", knob);
+    if (value < 0) return fail(SDRGPU_ERR_INVALID_ARG, "tuning values are >= 0");
+    g_tuning[knob] = value;
+    return SDRGPU_OK;
+}
+int sdrgpu_get_tuning(int knob) { return (knob < 0 || knob >= SDRGPU_TUNE_COUNT) ? -1 : g_tuning[knob]; }
 
 sdrgpu_status sdrgpu_device_count(int *count)
 {

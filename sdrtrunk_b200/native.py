@@ -79,6 +79,8 @@ PROTOTYPES = {
     "sdrgpu_memcpy": (C.c_int, [_vp, _vp, C.c_size_t, C.c_int, C.c_int]),
     "sdrgpu_device_synchronize": (C.c_int, []),
     "sdrgpu_launch_count": (C.c_uint64, []),
+    "sdrgpu_set_tuning": (C.c_int, [C.c_int, C.c_int]),
+    "sdrgpu_get_tuning": (C.c_int, [C.c_int]),
     "sdrgpu_design_sinc_m2_channelizer": (C.c_int, [C.c_double, C.c_int, C.c_int, _f32p, C.c_int, _i32p]),
     "sdrgpu_design_sinc_m2_synthesizer": (C.c_int, [C.c_double, C.c_double, C.c_int, C.c_int, _f32p, C.c_int, _i32p]),
     "sdrgpu_design_half_band": (C.c_int, [C.c_int, C.c_int, _f32p]),

@@ -664,6 +664,27 @@ def test_pipeline_result_is_independent_of_chunking_and_memory_space(gpu):
         assert all(np.array_equal(g, r) for g, r in zip(got, ref)), (chunks, dev)
 
 
+def test_pipeline_call_with_more_chunks_than_an_int_has_bits(gpu):
+    """a long host call cut into many small time chunks: the doubling ramp of leading chunk sizes must stop at the chunk
+    size (it once overflowed after 21 doublings and the call never returned); the dibits equal the single pass"""
+    from sdrtrunk_b200.dsp import Bank, ComplexPolyphaseChannelizerM2, Pipeline
+    m, n_ch = 96, 40 * 1024
+    rng = np.random.default_rng(46)
+    bins = [11]
+    base = [sg.c4fm(rng.integers(0, 4, int(n_ch * 0.096) + 8), carrier_offset=120.0, timing_phase=0.4, n_samples=n_ch,
+                    amplitude=0.05)]
+    x = sg.interleave(sg.multiplex(base, bins, m, n_ch) + sg.awgn(rng, n_ch * m // 2, 1e-3))
+    taps, fir = oracle.sinc_m2_channelizer(25000.0, m, 9), c4fm_taps()
+    out = []
+    for chunks in (1, 64):
+        chan = ComplexPolyphaseChannelizerM2(taps, 2400000, m, maxInputFloats=x.size)
+        chan.setChannels(bins)
+        pipe = Pipeline(chan, Bank.preset(gpu.PRESET_P25_C4FM, len(bins), 50000.0, fir, max_samples_per_call=n_ch))
+        pipe.setChunks(chunks)
+        out.append(pipe.process(x)[0])
+    assert out[0].size > 3500 and np.array_equal(out[0], out[1])
+
+
 def test_config3_shape_all_400_channels(gpu):
     """BASELINE configs[2] at full width: 10 MS/s, M = 400, every bin carries C4FM; all 400 channels through the fused
     pipeline.  Every channel must decode its transmitted dibits (size-independent property), and a sample of channels
