@@ -42,6 +42,8 @@ constexpr int kMaxEvents = 64;
 struct ChanParams {
     const float2 *state;  // [state_len] history ((2T-1)*M/2 samples) followed by the leftover samples
     const float2 *in;     // [n_in] new samples
+    const uint8_t *raw;   // pfb2_kernel<..., RAW>: the same samples as 8-bit tuner I/Q (2 bytes per complex sample), converted on load
+    int raw_flip, raw_bias;  // value = (int)(byte ^ raw_flip) - raw_bias: signed 8-bit (0x80, 128), unsigned (0, 127)
     const float *taps;    // [M*T] prototype filter h
     const float2 *tw;     // [M] e^{+j 2 pi k / M}
     const float2 *tw2;    // [R1][R2] e^{+j 2 pi n2 k1 / M}: the twiddles between the two steps of pfb2_kernel
@@ -68,13 +70,23 @@ struct ChanParams {
     int next_len, consumed;
 };
 
+// ByteSampleConverter / SignedByteSampleConverter (J/source/tuner/... lookup tables: (b - 127) / 128.0f, b / 128.0f): both
+// steps are exact in float, so converting on load gives the bits convert_kernel would have written
+__device__ __forceinline__ float2 load_raw(const ChanParams &p, long long idx)
+{
+    const uchar2 b = __ldg(reinterpret_cast<const uchar2 *>(p.raw) + idx);
+    const int vi = (int)(b.x ^ p.raw_flip) - p.raw_bias, vq = (int)(b.y ^ p.raw_flip) - p.raw_bias;
+    return make_float2(__fmul_rn((float)vi, 0.0078125f), __fmul_rn((float)vq, 0.0078125f));
+}
+
+template <bool RAW = false>
 __device__ __forceinline__ float2 load_x(const ChanParams &p, int unit, int r)
 {
     // virtual concatenation [state | in | zeros]; unit 0 starts right after the history
     int idx = p.H + unit * p.half + r;
     if (idx < p.state_len) return __ldg(p.state + idx);
     idx -= p.state_len;
-    if (idx < p.n_in) return __ldg(p.in + idx);
+    if (idx < p.n_in) return RAW ? load_raw(p, idx) : __ldg(p.in + idx);
     return make_float2(0.0f, 0.0f);
 }
 
@@ -307,9 +319,9 @@ struct Pfb2Layout {
     static constexpr size_t smem_bytes = sizeof(float2) * (size_t)(region0 + NB * YB);
 };
 
-template <int M, int NB, int TT, bool FAST>
-__device__ __forceinline__ void fb_thread(const ChanParams &p, const float2 *__restrict__ xin, int b0, int r, float2 *V,
-                                          int SV)
+template <int M, int NB, int TT, bool FAST, bool RAW>
+__device__ __forceinline__ void fb_thread(const ChanParams &p, const float2 *__restrict__ xin, long long first, int b0, int r,
+                                          float2 *V, int SV)
 {
     constexpr int half = M / 2;
     const int n = half - 1 - r;
@@ -322,7 +334,8 @@ __device__ __forceinline__ void fb_thread(const ChanParams &p, const float2 *__r
     float2 accA[NB], accB[NB];
 #pragma unroll
     for (int pp = NB - 1; pp >= -(2 * TT - 1); --pp) {
-        const float2 x = FAST ? __ldg(xin + (pp + 2 * TT - 1) * half + r) : load_x(p, b0 + pp, r);
+        const float2 x = !FAST ? load_x<RAW>(p, b0 + pp, r)
+                         : (RAW ? load_raw(p, first + (pp + 2 * TT - 1) * half + r) : __ldg(xin + (pp + 2 * TT - 1) * half + r));
 #pragma unroll
         for (int t = 0; t < TT; t++) {
             const int bl = pp + 2 * t;  // branch n: unit P = B - 2t
@@ -359,7 +372,7 @@ __device__ __forceinline__ void fb_thread(const ChanParams &p, const float2 *__r
     }
 }
 
-template <int M, int R1, int R2, int NB, int TT, int NT, int MINB>
+template <int M, int R1, int R2, int NB, int TT, int NT, int MINB, bool RAW>
 __global__ void __launch_bounds__(NT, MINB) pfb2_kernel(const ChanParams p)
 {
     using L = Pfb2Layout<M, R1, R2, NB, TT, NT>;
@@ -377,7 +390,7 @@ __global__ void __launch_bounds__(NT, MINB) pfb2_kernel(const ChanParams p)
             const int idx = p.consumed + i;
             float2 v = make_float2(0.0f, 0.0f);
             if (idx < p.state_len) v = p.state[idx];
-            else if (idx - p.state_len < p.n_in) v = p.in[idx - p.state_len];
+            else if (idx - p.state_len < p.n_in) v = RAW ? load_raw(p, idx - p.state_len) : p.in[idx - p.state_len];
             p.next_state[i] = v;
         }
     }
@@ -387,19 +400,22 @@ __global__ void __launch_bounds__(NT, MINB) pfb2_kernel(const ChanParams p)
         // every sample this tile needs lies in the new input (true for all but the first tiles of a call)
         const long long first = (long long)b0 * half - p.state_len;                    // index into p.in of unit b0-(2T-1)
         const bool fast = first >= 0 && first + (long long)(NB + 2 * TT - 1) * half <= p.n_in;
-        const float2 *xin = p.in + (fast ? first : 0);
+        const float2 *xin = RAW ? nullptr : p.in + (fast ? first : 0);
         {
             // pull the new input of the tile that will run about a wave later into L2: the first touch of every input
             // line otherwise costs the filter bank a DRAM round trip (+10 % measured)
             const long long ahead = first + (long long)(2 * TT - 1 + (long long)p.prefetch_blocks) * half;
-            const int lines = NB * half * (int)sizeof(float2) / 128;
+            const int lines = NB * half * (RAW ? 2 : (int)sizeof(float2)) / 128;
             if (ahead >= 0 && ahead + (long long)NB * half <= p.n_in)
-                for (int i = tid; i < lines; i += NT) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.in + ahead + i * 16));
+                for (int i = tid; i < lines; i += NT) {
+                    if (RAW) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.raw + 2 * ahead + i * 128));
+                    else asm volatile("prefetch.global.L2 [%0];" ::"l"(p.in + ahead + i * 16));
+                }
         }
         if (fast) {
-            for (int r = tid; r < half; r += NT) fb_thread<M, NB, TT, true>(p, xin, b0, r, V, SV);
+            for (int r = tid; r < half; r += NT) fb_thread<M, NB, TT, true, RAW>(p, xin, first, b0, r, V, SV);
         } else {
-            for (int r = tid; r < half; r += NT) fb_thread<M, NB, TT, false>(p, xin, b0, r, V, SV);
+            for (int r = tid; r < half; r += NT) fb_thread<M, NB, TT, false, RAW>(p, xin, first, b0, r, V, SV);
         }
     }
     __syncthreads();
@@ -762,6 +778,11 @@ struct sdrgpu_channelizer {
     int max_in_complex = 0, max_blocks = 0;
     int leftover = 0, parity0 = 0;
     bool throttled = false;   // chan_set_throttled: the pipeline is overlapping this launch with the demodulator
+    // chan_convert leaves 8-bit tuner samples unconverted for chan_enqueue: the M = 400 / 800 filter bank converts them on
+    // load (no float copy of the input in HBM); anything else converts them with convert_kernel first
+    const uint8_t *defer_src = nullptr;
+    const float2 *defer_dst = nullptr;
+    int defer_n = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaStream_t copy_in = nullptr, copy_out = nullptr;   // H2D / D2H streams of the chunked host path
     cudaEvent_t events[kMaxEvents] = {};
@@ -924,11 +945,11 @@ sdrgpu_status upload_selection(sdrgpu_channelizer *h)
     return SDRGPU_OK;
 }
 
-template <int M, int R1, int R2, int NB, int TT, int NT, int MINB>
+template <int M, int R1, int R2, int NB, int TT, int NT, int MINB, bool RAW = false>
 sdrgpu_status launch_pfb2(const sdrgpu_channelizer *h, const ChanParams &p)
 {
     using L = Pfb2Layout<M, R1, R2, NB, TT, NT>;
-    auto kernel = pfb2_kernel<M, R1, R2, NB, TT, NT, MINB>;
+    auto kernel = pfb2_kernel<M, R1, R2, NB, TT, NT, MINB, RAW>;
     // a pipeline that overlaps its time chunks with the demodulator holds the channelizer to a few CTAs per SM
     const size_t smem = (h->throttled || g_tuning[SDRGPU_TUNE_THROTTLE_ALWAYS]) ? smem_for_ctas_per_sm(L::smem_bytes, 0, g_tuning[SDRGPU_TUNE_PFB_CTAS_PER_SM]) : L::smem_bytes;
     SDRGPU_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > L::smem_bytes ? 227 * 1024 : L::smem_bytes)));
@@ -956,6 +977,15 @@ int sdrgpu::chan_selected_count(const sdrgpu_channelizer *h) { return h ? h->n_s
 
 // Enqueues the channelizer kernels for n_in device-resident complex samples on the handle's stream and updates the
 // host-side framing state (leftover samples, block parity, history ping-pong).  No copies, no synchronisation.
+static void launch_convert(sdrgpu_channelizer *h, const uint8_t *src, float2 *dst, int n)
+{
+    const size_t values = 2 * (size_t)n;
+    int grid = (int)((values + 255) / 256);
+    if (grid > 148 * 16) grid = 148 * 16;
+    convert_kernel<<<grid, 256, 0, h->stream>>>(h->in_format, src, reinterpret_cast<float *>(dst), values);
+    count_launch();
+}
+
 sdrgpu_status sdrgpu::chan_enqueue(sdrgpu_channelizer *h, const float2 *d_in, int n_in, float *d_out, long long stride,
                                    int layout, int *n_blocks_out)
 {
@@ -969,6 +999,11 @@ sdrgpu_status sdrgpu::chan_enqueue(sdrgpu_channelizer *h, const float2 *d_in, in
     const int new_len = h->H + new_leftover;
     float2 *next = h->d_state[h->cur_state ^ 1];
     bool state_saved = false;
+    // 8-bit samples chan_convert left unconverted: the filter bank reads them as they are when it runs, else convert now
+    const uint8_t *raw = (h->defer_src && d_in == h->defer_dst && n_in == h->defer_n) ? h->defer_src : nullptr;
+    h->defer_src = nullptr;
+    const bool fuse_convert = raw && n_blocks > 0 && h->fast_r1 && (h->M == 400 || h->M == 800);
+    if (raw && !fuse_convert) launch_convert(h, raw, const_cast<float2 *>(d_in), n_in);
     // checked before anything is launched or the framing state advances: a failing call leaves the handle as it was
     if (n_blocks > 0 && (h->n_mix > 0 || h->n_post > 0)) {
         // The reference rotates every channel's mixer for every buffer; the results layout has no per-channel rows to
@@ -982,6 +1017,9 @@ sdrgpu_status sdrgpu::chan_enqueue(sdrgpu_channelizer *h, const float2 *d_in, in
         ChanParams p{};
         p.state = state;
         p.in = d_in;
+        p.raw = fuse_convert ? raw : nullptr;
+        p.raw_flip = h->in_format == SDRGPU_FORMAT_S8 ? 0x80 : 0;
+        p.raw_bias = h->in_format == SDRGPU_FORMAT_S8 ? 128 : 127;
         p.taps = h->d_taps;
         p.tw = h->d_tw;
         p.tw2 = h->d_tw2;
@@ -1024,7 +1062,9 @@ sdrgpu_status sdrgpu::chan_enqueue(sdrgpu_channelizer *h, const float2 *d_in, in
         h->timer.begin(h->stream);
         sdrgpu_status st;
         // tile sizes measured on B200 (profiles/): M = 400 runs best as 8-block tiles, 200 threads, 4 CTAs per SM
-        if (h->fast_r1 && h->M == 400) st = launch_pfb2<400, 20, 20, 8, 9, 200, 4>(h, p);
+        if (fuse_convert && h->M == 400) st = launch_pfb2<400, 20, 20, 8, 9, 200, 4, true>(h, p);
+        else if (fuse_convert && h->M == 800) st = launch_pfb2<800, 32, 25, 8, 9, 256, 2, true>(h, p);
+        else if (h->fast_r1 && h->M == 400) st = launch_pfb2<400, 20, 20, 8, 9, 200, 4>(h, p);
         else if (h->fast_r1 && h->M == 800) st = launch_pfb2<800, 32, 25, 8, 9, 256, 2>(h, p);
         else if (h->fast_r1 && h->M == 96) st = launch_pfb2<96, 8, 12, 16, 9, 192, 2>(h, p);
         else if (h->fast_r1 && h->M == 640) st = launch_pfb2<640, 32, 20, 8, 9, 320, 2>(h, p);
@@ -1146,12 +1186,15 @@ const float2 *sdrgpu::chan_convert(sdrgpu_channelizer *h, const void *iq_device,
                            h->stream) != SDRGPU_OK)
             return nullptr;
     } else if (n > 0) {
-        const size_t values = 2 * (size_t)n;
-        int grid = (int)((values + 255) / 256);
-        if (grid > 148 * 16) grid = 148 * 16;
-        convert_kernel<<<grid, 256, 0, h->stream>>>(h->in_format, src + cb * first, reinterpret_cast<float *>(h->d_in + first),
-                                                    values);
-        count_launch();
+        const bool eight_bit = h->in_format == SDRGPU_FORMAT_U8 || h->in_format == SDRGPU_FORMAT_S8;
+        static const int fuse_env = getenv("SDRGPU_FUSE_CONVERT") ? atoi(getenv("SDRGPU_FUSE_CONVERT")) : 1;
+        if (fuse_env && eight_bit && h->fast_r1 && (h->M == 400 || h->M == 800)) {
+            h->defer_src = src + cb * first;
+            h->defer_dst = h->d_in + first;
+            h->defer_n = n;
+        } else {
+            launch_convert(h, src + cb * first, h->d_in + first, n);
+        }
     }
     return h->d_in + first;
 }

@@ -277,15 +277,18 @@ def test_frequency_corrected_channels_oscillator_look_ahead_is_bit_exact(gpu):
                 break
 
 
+@pytest.mark.parametrize("m", [96, 400, 800])
 @pytest.mark.parametrize("fmt", ["u8", "s8", "s16le"])
-def test_native_tuner_sample_formats(gpu, fmt):
+def test_native_tuner_sample_formats(gpu, fmt, m):
     """section 8f #1: ByteSampleConverter / SignedByteSampleConverter / 16-bit conversion on the device, standalone
-    (bit-exact: integer / power of two, or one correctly rounded division) and fused in front of the channelizer."""
+    (bit-exact: integer / power of two, or one correctly rounded division) and fused in front of the channelizer.  For
+    M = 400 / 800 the filter bank itself reads the 8-bit samples (no float copy of the input): ragged calls cover its
+    tiles that reach into the float history, a call shorter than one block (converted by the stand-alone kernel) and the
+    history the kernel saves from raw samples."""
     from sdrtrunk_b200.dsp import (ByteSampleConverter, ComplexPolyphaseChannelizerM2, Signed16BitSampleConverter,
                                    SignedByteSampleConverter)
     rng = np.random.default_rng(31)
-    m = 96
-    n = 48 * 300
+    n = m // 2 * 300
     if fmt == "u8":
         raw = rng.integers(0, 256, 2 * n, dtype=np.uint8)
         conv = ByteSampleConverter()
@@ -303,7 +306,8 @@ def test_native_tuner_sample_formats(gpu, fmt):
     taps = oracle.sinc_m2_channelizer(25000.0, m, 9)
     ch = ComplexPolyphaseChannelizerM2(taps, 25000 * m, m)
     ch.setSampleFormat(fmt)
-    got = np.concatenate([ch.receive(raw[:10000]), ch.receive(raw[10000:])])
+    got = np.concatenate([ch.receive(raw[:10000]), ch.receive(raw[10000:10050]), ch.receive(raw[10050:10050 + 34 * m]),
+                          ch.receive(raw[10050 + 34 * m:])])
     ref = ComplexPolyphaseChannelizerM2(taps, 25000 * m, m).receive(want_f)       # same kernels on converted floats
     assert np.array_equal(got, ref)
     assert sg.rel_rms(got, oracle.Channelizer(taps, m).receive(want_f, mode="f64")) < TOL
