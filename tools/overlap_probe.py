@@ -24,8 +24,8 @@ def main():
     _, timed = bench.make_timed(torch, dist, dev, 1)
     inputs = bench.TunerInputs(torch, dev, "c4fm_20m", 0, tuners)
     w = bench.TunerWorkload("c4fm_20m", inputs, tuners, 0)
-    grid = [(1, 0, 0), (4, 0, 0), (8, 0, 0), (16, 0, 0)]
-    for chunks in (4, 8, 16):
+    grid = [(1, 0, 0), (2, 0, 0), (3, 0, 0), (4, 0, 0), (6, 0, 0), (8, 0, 0), (12, 0, 0), (16, 0, 0), (4, 0, 0), (8, 0, 0)]
+    for chunks in ():
         for fir in (1, 2, 3, 4):
             grid.append((chunks, fir, 0))
         for fir, pfb in ((1, 1), (2, 1), (3, 1)):
