@@ -307,8 +307,9 @@ enum {
 };
 sdrgpu_status sdrgpu_bank_set_sync_detector(sdrgpu_bank *b, int kind);
 /* Tuning: how many lanes of a warp work on one channel in the symbol demodulator kernel -- 32 (one warp per channel),
- * 16 (two channels per warp), 8 / 4 (four / eight channels per warp; not with SDRGPU_SYNC_P25_PHASE1 / _PHASE2),
- * 1 (one thread per channel), 0 = chosen from the bank size (default).  All variants do
+ * 16 (two channels per warp), 8 / 4 / 2 (four / eight / sixteen channels per warp, several samples of a symbol period per
+ * lane; with a sync detector: 8 / 4 for Phase 1 sync and for Phase 2 sync behind the Gardner demodulator, other
+ * combinations run two channels per warp), 1 (one thread per channel), 0 = chosen from the bank size (default).  All variants do
  * the same arithmetic on the same per-channel state; the result does not depend on the choice, which may change
  * between calls -- except while a sync detector (SDRGPU_SYNC_P25_PHASE1 / _PHASE2) is enabled: choose the layout first
  * (SDRGPU_ERR_BAD_STATE otherwise). */

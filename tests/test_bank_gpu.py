@@ -274,7 +274,8 @@ def _sync_case(kind, rng, n, offset, with_sync=True):
     return sg.interleave(z + sg.awgn(rng, n, 0.01))
 
 
-@pytest.mark.parametrize("kind,lanes", [("c4fm", 0), ("lsm", 0), ("hdqpsk", 0), ("c4fm", 16), ("hdqpsk", 16), ("lsm", 1)])
+@pytest.mark.parametrize("kind,lanes", [("c4fm", 0), ("lsm", 0), ("hdqpsk", 0), ("c4fm", 16), ("hdqpsk", 16), ("lsm", 1),
+                                        ("c4fm", 8), ("c4fm", 4), ("lsm", 8), ("lsm", 4), ("hdqpsk", 8), ("hdqpsk", 4)])
 def test_sync_detector_and_inversion_feedback_on_device(gpu, kind, lanes):
     """the framer's sync detector + PLLPhaseInversionDetector feedback run inside the demodulator
     kernel.  Channels locked 90 / 180 degrees off (carrier offset = +-rate/4, rate/2) must be corrected at the very
@@ -473,7 +474,7 @@ def test_demodulator_layout_can_change_between_calls(gpu):
     with pytest.raises(gpu.IllegalStateException):
         bank.setDemodulatorLanes(1)
     with pytest.raises(gpu.IllegalStateException):
-        bank.setDemodulatorLanes(8)                         # the batched sync matcher needs 16 lanes per channel
+        bank.setDemodulatorLanes(8)                         # (psk_multi_kernel's per-symbol matcher keeps the thread kernel's state)
 
 
 # ------------------------------------------------------------------------------------------------ pipeline
