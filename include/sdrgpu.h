@@ -314,6 +314,15 @@ sdrgpu_status sdrgpu_bank_set_sync_detector(sdrgpu_bank *b, int kind);
  * between calls -- except while a sync detector (SDRGPU_SYNC_P25_PHASE1 / _PHASE2) is enabled: choose the layout first
  * (SDRGPU_ERR_BAD_STATE otherwise). */
 sdrgpu_status sdrgpu_bank_set_demodulator_lanes(sdrgpu_bank *b, int lanes_per_channel);
+/* Per-symbol tap points of ONE channel of the bank, the listeners of DQPSKDecisionDirectedDemodulatorInstrumented /
+ * DQPSKGardnerDemodulatorInstrumented (J/dsp/psk/DQPSKDecisionDirectedDemodulatorInstrumented.java:74-108: complex symbol,
+ * samples per symbol, PLL error, PLL frequency).  While a tap is set (channel >= 0; -1 clears it) every process call also
+ * demodulates that channel from a copy of its states on a side stream, recording per symbol 6 doubles
+ * {symbol_i, symbol_q, detected samples per symbol, loop frequency in radians per sample, sampling point, PLL error} as
+ * they are at the end of calculateSymbol(); the bank's own launch and results are not affected.
+ * sdrgpu_bank_read_symbol_tap returns the symbols of the last process call (values[6 * capacity_symbols]). */
+sdrgpu_status sdrgpu_bank_set_symbol_tap(sdrgpu_bank *b, int channel);
+sdrgpu_status sdrgpu_bank_read_symbol_tap(sdrgpu_bank *b, double *values, int capacity_symbols, int *n_symbols);
 /* loop state tap points of one channel: {pll phase, pll frequency, sampling point, detected samples/symbol} */
 sdrgpu_status sdrgpu_bank_get_loop_state(sdrgpu_bank *b, int channel, double *state4);
 /* 4 dibits per byte MSB first (J/dsp/symbol/DibitToByteBufferAssembler.java:58-93); host helper */

@@ -83,6 +83,11 @@ public final class SdrGpu
     static final MethodHandle BANK_CORRECT_INVERSION = h("sdrgpu_bank_correct_inversion",
         FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, JAVA_DOUBLE));
     static final MethodHandle BANK_SET_SYNC_DETECTOR = h("sdrgpu_bank_set_sync_detector", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT));
+    /** the listeners of DQPSKDecisionDirectedDemodulatorInstrumented for one channel of a bank: (bank, channel | -1) */
+    static final MethodHandle BANK_SET_SYMBOL_TAP = h("sdrgpu_bank_set_symbol_tap", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT));
+    /** (bank, double[6 * capacity] values, capacity, int[1] nSymbols): symbol I, Q, samples per symbol, loop frequency, sampling point, PLL error */
+    static final MethodHandle BANK_READ_SYMBOL_TAP = h("sdrgpu_bank_read_symbol_tap",
+        FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, ADDRESS));
     static final MethodHandle PIPELINE_CREATE_MULTI = h("sdrgpu_pipeline_create_multi",
         FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, ADDRESS));
     static final MethodHandle PIPELINE_DESTROY = h("sdrgpu_pipeline_destroy", FunctionDescriptor.of(JAVA_INT, ADDRESS));

@@ -96,7 +96,7 @@ def lib():
         "orc_agc_block": (None, [_f32p, C.c_int, _f32p]),
         "orc_psk_create": (vp, [C.c_int, C.c_double, C.c_double, C.c_double, C.c_float]),
         "orc_psk_destroy": (None, [vp]),
-        "orc_psk_receive": (C.c_int, [vp, _f32p, C.c_int, _u8p, _f32p]),
+        "orc_psk_receive": (C.c_int, [vp, _f32p, C.c_int, _u8p, C.POINTER(C.c_double)]),
         "orc_psk_correct_inversion": (None, [vp, C.c_double]),
         "orc_airspy_create": (vp, []),
         "orc_airspy_destroy": (None, [vp]),
@@ -502,9 +502,9 @@ class PSKDemodulator:
         a, p = _f32(iq)
         cap = a.size // 2 // 4 + 8
         dibits = np.zeros(cap, np.uint8)
-        taps = np.zeros((cap, 4), np.float32) if want_taps else None
+        taps = np.zeros((cap, 6), np.float64) if want_taps else None
         n = lib().orc_psk_receive(self._h, p, a.size, dibits.ctypes.data_as(_u8p),
-                                  taps.ctypes.data_as(_f32p) if want_taps else None)
+                                  taps.ctypes.data_as(C.POINTER(C.c_double)) if want_taps else None)
         return (dibits[:n], taps[:n]) if want_taps else dibits[:n]
 
     def correct_inversion(self, correction):

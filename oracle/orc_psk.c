@@ -188,7 +188,7 @@ static float slice(const orc_psk *p, cpx cur, int *dibit, int *use_less_than)
 }
 
 /* DQPSKDecisionDirectedDemodulator.java:50-89 */
-static int calculate_symbol_dd(orc_psk *p, float *taps)
+static int calculate_symbol_dd(orc_psk *p, double *taps)
 {
     /* InterpolatingSampleBuffer.java:148-165 */
     cpx preceding = {p->delay_i[p->pointer + 3], p->delay_q[p->pointer + 3]};
@@ -212,17 +212,19 @@ static int calculate_symbol_dd(orc_psk *p, float *taps)
     pll_adjust(p, (double)clipf(phase_error, 0.5f));
     p->prev_a = preceding;
     p->prev_b = current;
-    if (taps) {
+    if (taps) { /* the tap points of DQPSK*DemodulatorInstrumented.java:74-108, taken at the end of calculateSymbol */
         taps[0] = cur_sym.i;
         taps[1] = cur_sym.q;
         taps[2] = p->detected_sps;
-        taps[3] = (float)p->loop_frequency;
+        taps[3] = p->loop_frequency;
+        taps[4] = p->sampling_point;
+        taps[5] = phase_error;
     }
     return dibit;
 }
 
 /* DQPSKGardnerDemodulator.java:48-89 ; DQPSKGardnerSymbolEvaluator.java:61-105 */
-static int calculate_symbol_gardner(orc_psk *p, float *taps)
+static int calculate_symbol_gardner(orc_psk *p, double *taps)
 {
     /* the two roles are flip-flopped on purpose (DQPSKGardnerDemodulator.java:50-57) */
     cpx middle = {interp_at(p, p->delay_i, p->sampling_point), interp_at(p, p->delay_q, p->sampling_point)};
@@ -249,17 +251,19 @@ static int calculate_symbol_gardner(orc_psk *p, float *taps)
     pll_adjust(p, (double)phase_error);
     p->prev_a = middle;
     p->prev_b = current;
-    if (taps) {
+    if (taps) { /* the tap points of DQPSK*DemodulatorInstrumented.java:74-108, taken at the end of calculateSymbol */
         taps[0] = cur_sym.i;
         taps[1] = cur_sym.q;
         taps[2] = p->detected_sps;
-        taps[3] = (float)p->loop_frequency;
+        taps[3] = p->loop_frequency;
+        taps[4] = p->sampling_point;
+        taps[5] = phase_error;
     }
     return dibit;
 }
 
 /* PSKDemodulator.java:83-117 */
-int orc_psk_receive(orc_psk *p, const float *iq, int n_floats, uint8_t *dibits, float *taps)
+int orc_psk_receive(orc_psk *p, const float *iq, int n_floats, uint8_t *dibits, double *taps)
 {
     int n_symbols = 0;
     for (int x = 0; x < n_floats; x += 2) {
@@ -282,7 +286,7 @@ int orc_psk_receive(orc_psk *p, const float *iq, int n_floats, uint8_t *dibits, 
         p->pointer = p->pointer % p->twice_sps;
 
         if (p->sampling_point < 1.0f) {
-            float *t = taps ? taps + 4 * (size_t)n_symbols : NULL;
+            double *t = taps ? taps + 6 * (size_t)n_symbols : NULL;
             int d = (p->kind == ORC_PSK_GARDNER) ? calculate_symbol_gardner(p, t) : calculate_symbol_dd(p, t);
             /* calculateSymbol ends with broadcast(dibit): the framer's sync detector runs synchronously and may call
              * correctInversion before the next sample is processed (P25P1SyncDetector.java:150-154) */

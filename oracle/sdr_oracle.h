@@ -178,8 +178,9 @@ orc_psk *orc_psk_create(int kind, double sample_rate, double symbol_rate, double
                         float sample_counter_gain);
 void orc_psk_destroy(orc_psk *p);
 /* feeds n_floats interleaved I/Q; writes one byte per symbol (Dibit.getValue 0..3); returns symbol count.
- * taps (optional, may be NULL): per symbol 4 floats {soft_i, soft_q, detected_sps, pll_frequency} */
-int orc_psk_receive(orc_psk *p, const float *iq, int n_floats, uint8_t *dibits, float *taps);
+ * taps (optional, may be NULL): per symbol 6 doubles {soft_i, soft_q, detected_sps, pll_frequency (radians per sample),
+ * sampling_point, pll_error}: the listener tap points of DQPSKDecisionDirectedDemodulatorInstrumented.java:74-108 */
+int orc_psk_receive(orc_psk *p, const float *iq, int n_floats, uint8_t *dibits, double *taps);
 void orc_psk_correct_inversion(orc_psk *p, double correction);
 void orc_psk_reset_pll(orc_psk *p);
 void orc_psk_get_state(const orc_psk *p, double *phase, double *freq, float *sampling_point, float *detected_sps);

@@ -1399,13 +1399,38 @@ sdrgpu_status sdrgpu_convert_samples(int format, const void *src, int src_mem, i
     if (n_values < 0 || (n_values > 0 && (!src || !dst))) return fail(SDRGPU_ERR_INVALID_ARG, "NULL / negative argument");
     if (n_values == 0) return SDRGPU_OK;
     const size_t vb = format == SDRGPU_FORMAT_S16LE ? 2 : 1;
+    // device staging for host buffers: kept per host thread and grown on demand (a converter is called once per tuner
+    // buffer; an allocation per call would cost more than the conversion)
+    struct Staging {
+        void *p = nullptr;
+        size_t cap = 0;
+        int device = -1;
+        cudaError_t ensure(size_t bytes)
+        {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            if (p && (dev != device || bytes > cap)) {
+                cudaFree(p);
+                p = nullptr;
+            }
+            if (p) return cudaSuccess;
+            device = dev;
+            cap = bytes;
+            return cudaMalloc(&p, bytes);
+        }
+    };
+    static thread_local Staging stage_src, stage_dst;
     void *d_src = const_cast<void *>(src);
     float *d_dst = dst;
     if (src_mem == SDRGPU_HOST) {
-        SDRGPU_CUDA(cudaMalloc(&d_src, vb * (size_t)n_values));
+        SDRGPU_CUDA(stage_src.ensure(vb * (size_t)n_values));
+        d_src = stage_src.p;
         SDRGPU_CUDA(cudaMemcpy(d_src, src, vb * (size_t)n_values, cudaMemcpyHostToDevice));
     }
-    if (dst_mem == SDRGPU_HOST) SDRGPU_CUDA(cudaMalloc(&d_dst, sizeof(float) * (size_t)n_values));
+    if (dst_mem == SDRGPU_HOST) {
+        SDRGPU_CUDA(stage_dst.ensure(sizeof(float) * (size_t)n_values));
+        d_dst = static_cast<float *>(stage_dst.p);
+    }
     int grid = (n_values + 255) / 256;
     if (grid > 148 * 16) grid = 148 * 16;
     convert_kernel<<<grid, 256>>>(format, d_src, d_dst, (size_t)n_values);
@@ -1413,8 +1438,6 @@ sdrgpu_status sdrgpu_convert_samples(int format, const void *src, int src_mem, i
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess && dst_mem == SDRGPU_HOST) e = cudaMemcpy(dst, d_dst, sizeof(float) * (size_t)n_values, cudaMemcpyDeviceToHost);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
-    if (src_mem == SDRGPU_HOST) cudaFree(d_src);
-    if (dst_mem == SDRGPU_HOST) cudaFree(d_dst);
     if (e != cudaSuccess) return fail(SDRGPU_ERR_CUDA, "sample conversion failed: %s", cudaGetErrorString(e));
     return SDRGPU_OK;
 }

@@ -150,6 +150,24 @@ class Bank:
     def resetPLL(self, channel):
         native.check(native.lib().sdrgpu_bank_reset_pll(self._h, int(channel)))
 
+    def setSymbolTap(self, channel):
+        """Per-symbol tap points of one channel (the listeners of DQPSKDecisionDirectedDemodulatorInstrumented /
+        DQPSKGardnerDemodulatorInstrumented: setComplexSymbolListener, setSamplesPerSymbolListener, setPLLErrorListener,
+        setPLLFrequencyListener); None / -1 clears it."""
+        native.check(native.lib().sdrgpu_bank_set_symbol_tap(self._h, -1 if channel is None else int(channel)))
+
+    def symbolTap(self, sampleRate=None):
+        """float64 [n_symbols, 6] of the last process call: symbol I, symbol Q, detected samples per symbol, PLL frequency
+        (radians per sample; in Hz when sampleRate is given, as the Java's listener reports it), sampling point, PLL error"""
+        cap = 1 << 16
+        out = np.zeros((cap, 6), np.float64)
+        n = C.c_int(0)
+        native.check(native.lib().sdrgpu_bank_read_symbol_tap(self._h, out.ctypes.data_as(C.POINTER(C.c_double)), cap, C.byref(n)))
+        out = out[:n.value].copy()
+        if sampleRate is not None:
+            out[:, 3] *= float(sampleRate) / (2.0 * np.pi)
+        return out
+
     def loopState(self, channel):
         st = (C.c_double * 4)()
         native.check(native.lib().sdrgpu_bank_get_loop_state(self._h, int(channel), st))

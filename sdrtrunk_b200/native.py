@@ -118,6 +118,8 @@ PROTOTYPES = {
     "sdrgpu_bank_correct_inversion": (C.c_int, [_vp, C.c_int, C.c_double]),
     "sdrgpu_bank_set_sync_detector": (C.c_int, [_vp, C.c_int]),
     "sdrgpu_bank_set_demodulator_lanes": (C.c_int, [_vp, C.c_int]),
+    "sdrgpu_bank_set_symbol_tap": (C.c_int, [_vp, C.c_int]),
+    "sdrgpu_bank_read_symbol_tap": (C.c_int, [_vp, C.POINTER(C.c_double), C.c_int, _i32p]),
     "sdrgpu_bank_reset_pll": (C.c_int, [_vp, C.c_int]),
     "sdrgpu_bank_get_loop_state": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_double)]),
     "sdrgpu_pack_dibits": (C.c_int, [_u8p, C.c_int, _u8p]),

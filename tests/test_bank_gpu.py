@@ -317,6 +317,61 @@ def test_sync_detector_and_inversion_feedback_on_device(gpu, kind, lanes):
         bank2.setSyncDetector(7)
 
 
+@pytest.mark.parametrize("kind,lanes,sync", [("c4fm", 0, False), ("c4fm", 4, False), ("c4fm", 32, True), ("c4fm", 4, True),
+                                             ("lsm", 0, False), ("hdqpsk", 16, True), ("hdqpsk", 1, False)])
+def test_symbol_tap_matches_the_instrumented_demodulator(gpu, kind, lanes, sync):
+    """SURVEY section 5 / DQPSK*DemodulatorInstrumented: the per-symbol tap of one channel of a bank (complex symbol, samples
+    per symbol, PLL frequency, sampling point, PLL error) equals the oracle demodulator's taps on the same FIR / AGC output,
+    for every kernel family, with and without the sync detector's inversion feedback, across ragged calls and a tap moved
+    to another channel; the bank's own dibits do not change."""
+    from sdrtrunk_b200.dsp import Bank
+    preset, okind, taps = _preset(gpu, kind)
+    gardner, rate, bw, gain = {"c4fm": (False, 4800.0, 300.0, 0.3), "lsm": (True, 4800.0, 200.0, 0.3),
+                               "hdqpsk": (True, 6000.0, 300.0, 0.1)}[kind]
+    skind, okind_sync = ((gpu.SYNC_P25_PHASE2, oracle.SYNC_P25_PHASE2) if kind == "hdqpsk"
+                         else (gpu.SYNC_P25_PHASE1, oracle.SYNC_P25_PHASE1))
+    rng = np.random.default_rng(61)
+    n = 12 * 1024
+    offsets = [40.0, rate / 4 - 50, -80.0, rate / 2 - 100, 10.0]
+    x = np.stack([_sync_case(kind, rng, n, off) for off in offsets])
+    bank = Bank.preset(preset, len(offsets), 50000.0, taps, max_samples_per_call=8 * 1024)
+    bank.setDemodulatorLanes(lanes)
+    if sync:
+        bank.setSyncDetector(skind)
+    plain = Bank.preset(preset, len(offsets), 50000.0, taps, max_samples_per_call=8 * 1024)
+    plain.setDemodulatorLanes(lanes)
+    if sync:
+        plain.setSyncDetector(skind)
+    refs = []
+    for _ in offsets:
+        d = oracle.PSKDemodulator(oracle.GARDNER if gardner else oracle.DECISION_DIRECTED, 50000.0, rate, bw, gain)
+        if sync:
+            d.attach_sync(oracle.SyncDetector(okind_sync, 50000.0))
+        refs.append(d)
+    tapped = 1
+    bank.setSymbolTap(tapped)
+    for i, (a, b) in enumerate(((0, 4096), (4096, 5000), (5000, 9192), (9192, n))):
+        if i == 2:
+            tapped = 3
+            bank.setSymbolTap(tapped)
+        dib, filt = bank.process(x[:, 2 * a:2 * b], want_filtered=True)
+        want_dib = plain.process(x[:, 2 * a:2 * b])
+        tap = bank.symbolTap()
+        for k in range(len(offsets)):
+            assert np.array_equal(dib[k], want_dib[k]), (i, k)
+            ref_dib, ref_tap = refs[k].receive(filt[k], want_taps=True)
+            assert np.array_equal(dib[k], ref_dib), (i, k)
+            if k == tapped:
+                assert tap.shape == ref_tap.shape and (tap.shape[0] > 300 or i == 1), (i, tap.shape, ref_tap.shape)
+                assert np.array_equal(tap[:, [0, 1, 2, 4, 5]], ref_tap[:, [0, 1, 2, 4, 5]]), i
+                assert np.array_equal(tap[:, 3], ref_tap[:, 3]), i          # loop frequency: the same doubles
+    hz = bank.symbolTap(sampleRate=50000.0)
+    assert np.allclose(hz[:, 3], tap[:, 3] * 50000.0 / (2 * np.pi))
+    bank.setSymbolTap(None)
+    with pytest.raises(gpu.IllegalStateException):
+        bank.symbolTap()
+
+
 def _p2_channel(rng, n, offset, holes=()):
     """HDQPSK channel with the Phase 2 sync pattern every 180 symbols (every ISCH a sync ISCH), optional noise holes"""
     n_sym = int(n * 6000 / 50000) + 8
