@@ -66,6 +66,11 @@ struct ChanParams {
     int n_factors;
     int factors[kMaxFactors];
     unsigned magic_s[kMaxFactors];  // ceil(2^32 / s) for the stride of each pass
+    // pfb2_kernel, every bin a frequency-corrected one-bin channel (OneChannelOutputProcessor + Oscillator) with one
+    // float-representable gain: mixed where step B stores the rows.  osc = the look-ahead rings [M][osc_ring_len]
+    // (osc_produce_kernel; row == bin == oscillator), osc_start = ring slot of this call's first block; else nullptr
+    const float2 *osc;
+    int osc_ring_len, osc_start;
     float2 *next_state;  // pfb2_kernel only: one CTA also writes the next call's history (else save_state_kernel)
     int next_len, consumed;
 };
@@ -462,13 +467,34 @@ __global__ void __launch_bounds__(NT, MINB) pfb2_kernel(const ChanParams p)
                 const float inv = p.inv_m, g = p.gain_uniform;
                 float *o = p.out + (size_t)k1 * p.out_stride + 2 * (size_t)(b0 + b);
                 const size_t ostep = (size_t)R1 * p.out_stride;
+                if (p.osc != nullptr) {
+                    // every bin frequency-corrected (OneChannelOutputProcessor + Oscillator, row == bin == oscillator): the
+                    // oscillator value of this block from the look-ahead rings, multiplied in between the 1/M of the inverse
+                    // FFT and the gain -- the arithmetic of osc_mix_kernel on the value it would have read back
+                    int slot = p.osc_start + b0 + b;
+                    if (slot >= p.osc_ring_len) slot -= p.osc_ring_len;
+                    const float2 *zp = p.osc + (size_t)k1 * p.osc_ring_len + slot;
+                    const size_t zstep = (size_t)R1 * p.osc_ring_len;
 #pragma unroll
-                for (int k2 = 0; k2 < R2; k2++) {
-                    float2 v = a[k2];
-                    v.x = __fmul_rn(__fmul_rn(v.x, inv), g);
-                    v.y = __fmul_rn(__fmul_rn(v.y, inv), g);
-                    *reinterpret_cast<float2 *>(o) = v;
-                    o += ostep;
+                    for (int k2 = 0; k2 < R2; k2++) {
+                        const float2 z = __ldg(zp);
+                        const float vx = __fmul_rn(a[k2].x, inv), vy = __fmul_rn(a[k2].y, inv);
+                        float2 v;
+                        v.x = __fmul_rn(__fsub_rn(__fmul_rn(vx, z.x), __fmul_rn(vy, z.y)), g);
+                        v.y = __fmul_rn(__fadd_rn(__fmul_rn(vy, z.x), __fmul_rn(vx, z.y)), g);
+                        *reinterpret_cast<float2 *>(o) = v;
+                        o += ostep;
+                        zp += zstep;
+                    }
+                } else {
+#pragma unroll
+                    for (int k2 = 0; k2 < R2; k2++) {
+                        float2 v = a[k2];
+                        v.x = __fmul_rn(__fmul_rn(v.x, inv), g);
+                        v.y = __fmul_rn(__fmul_rn(v.y, inv), g);
+                        *reinterpret_cast<float2 *>(o) = v;
+                        o += ostep;
+                    }
                 }
             }
         } else {
@@ -807,6 +833,10 @@ struct sdrgpu_channelizer {
     float *d_out = nullptr;    // staging for host output
     size_t d_out_bytes = 0;
     int n_sel = 0;
+    // every bin selected in order as a frequency-corrected one-bin channel with one float-representable gain (the usual
+    // sdrtrunk situation when all channels of a tuner are in use): pfb2_kernel mixes the oscillators in where it stores
+    int mix_identity = 0;
+    float mix_gain = 0.0f;
     int *d_sel = nullptr;
     float *d_gain_f = nullptr;
     double *d_gain_d = nullptr;
@@ -878,6 +908,11 @@ sdrgpu_status upload_selection(sdrgpu_channelizer *h)
             gf.push_back(1.0f);
         }
     const int rows = (int)sel.size();
+    h->mix_identity = (int)mix.size() == n && n == h->M && rows == n;
+    for (size_t m = 0; m < mix.size() && h->mix_identity; m++)
+        if (mix[m].row != (int)m || sel[m] != (int)m || mix[m].gain != mix[0].gain || (double)(float)mix[m].gain != mix[m].gain)
+            h->mix_identity = 0;
+    h->mix_gain = mix.empty() ? 0.0f : (float)mix[0].gain;
     cudaFree(h->d_sel);
     cudaFree(h->d_gain_f);
     cudaFree(h->d_gain_d);
@@ -1013,7 +1048,35 @@ sdrgpu_status sdrgpu::chan_enqueue(sdrgpu_channelizer *h, const float2 *d_in, in
         if (h->n_mix > 0 && n_blocks > h->osc_ring_len)
             return fail(SDRGPU_ERR_OVERFLOW, "%d blocks exceed the oscillator look-ahead", n_blocks);
     }
+    // Frequency-corrected one-bin channels: the oscillator values come from the look-ahead rings (osc_produce_kernel on a
+    // side stream).  When every bin is such a channel pfb2_kernel multiplies them in where it stores the rows (no separate
+    // pass over the channel streams); otherwise the rows leave the kernel at gain 1 and osc_mix_kernel finishes them.
+    static const int fuse_mix_env = getenv("SDRGPU_FUSE_MIX") ? atoi(getenv("SDRGPU_FUSE_MIX")) : 1;
+    // (pfb2_kernel instances with 8-block tiles store straight from step B: M = 160 ... 800, see the launch table below)
+    const bool direct_store = h->fast_r1 && (h->M == 800 || h->M == 640 || h->M == 400 || h->M == 320 || h->M == 240 ||
+                                             h->M == 200 || h->M == 160);
+    const bool fused_mix = fuse_mix_env && h->n_mix > 0 && h->mix_identity && direct_store &&
+                           layout == SDRGPU_LAYOUT_CHANNELS && n_blocks > 0;
+    auto ensure_osc = [&]() -> sdrgpu_status {
+        const int pgrid = (h->n_mix + 31) / 32;
+        const long long have = h->osc_produced - h->osc_consumed;
+        // wait for the top-up in flight only if this call reaches into what it writes (or has to produce itself)
+        if (h->osc_pending && (h->osc_consumed + n_blocks > h->osc_safe || have < n_blocks)) {
+            SDRGPU_CUDA(cudaStreamWaitEvent(h->stream, h->ev_osc, 0));
+            h->osc_pending = false;
+            h->osc_safe = h->osc_produced;
+        }
+        if (have < n_blocks) {  // first call, or a call longer than the look-ahead: produce the rest in line
+            osc_produce_kernel<<<pgrid, 32, 0, h->stream>>>(h->d_mix, h->d_mix_state, h->d_osc, h->osc_ring_len,
+                                                           h->osc_produced, (int)(n_blocks - have), h->n_mix);
+            h->osc_produced += n_blocks - have;
+            h->osc_safe = h->osc_produced;
+            count_launch();
+        }
+        return SDRGPU_OK;
+    };
     if (n_blocks > 0) {
+        if (fused_mix) SDRGPU_TRY(ensure_osc());
         ChanParams p{};
         p.state = state;
         p.in = d_in;
@@ -1042,10 +1105,13 @@ sdrgpu_status sdrgpu::chan_enqueue(sdrgpu_channelizer *h, const float2 *d_in, in
         p.n_sel = h->n_rows;
         p.layout = layout;
         p.gain_exact = h->gain_exact;
-        p.identity = h->identity;
+        p.identity = fused_mix ? 1 : h->identity;   // (every bin in order, one gain: the direct store path, with the mix)
+        p.osc = fused_mix ? h->d_osc : nullptr;
+        p.osc_ring_len = h->osc_ring_len;
+        p.osc_start = fused_mix ? (int)(h->osc_consumed % h->osc_ring_len) : 0;
         static const int pf_waves = getenv("SDRGPU_PFB_PREFETCH") ? atoi(getenv("SDRGPU_PFB_PREFETCH")) : 2;
         p.prefetch_blocks = 148 * 8 * pf_waves;   // in quarter waves of 148 SMs x 4 CTAs x 8 blocks
-        p.gain_uniform = h->gain_uniform;
+        p.gain_uniform = fused_mix ? h->mix_gain : h->gain_uniform;
         p.inv_m = 1.0f / (float)h->M;
         p.n_factors = (int)h->factors.size();
         for (int i = 0; i < p.n_factors; i++) {
@@ -1086,36 +1152,23 @@ sdrgpu_status sdrgpu::chan_enqueue(sdrgpu_channelizer *h, const float2 *d_in, in
             SDRGPU_CUDA(cudaGetLastError());
         }
         if (layout == SDRGPU_LAYOUT_CHANNELS && h->n_mix > 0) {
-            const int pgrid = (h->n_mix + 31) / 32;
-            const long long have = h->osc_produced - h->osc_consumed;
-            // wait for the top-up in flight only if this call reaches into what it writes (or has to produce itself)
-            if (h->osc_pending && (h->osc_consumed + n_blocks > h->osc_safe || have < n_blocks)) {
-                SDRGPU_CUDA(cudaStreamWaitEvent(h->stream, h->ev_osc, 0));
-                h->osc_pending = false;
-                h->osc_safe = h->osc_produced;
-            }
-            if (have < n_blocks) {  // first call, or a call longer than the look-ahead: produce the rest in line
-                osc_produce_kernel<<<pgrid, 32, 0, h->stream>>>(h->d_mix, h->d_mix_state, h->d_osc, h->osc_ring_len,
-                                                               h->osc_produced, (int)(n_blocks - have), h->n_mix);
-                h->osc_produced += n_blocks - have;
-                h->osc_safe = h->osc_produced;
+            if (!fused_mix) {
+                SDRGPU_TRY(ensure_osc());
+                osc_mix_kernel<<<dim3((n_blocks + 255) / 256, h->n_mix), 256, 0, h->stream>>>(d_out, stride, h->d_mix, h->d_osc,
+                                                                                              h->osc_ring_len, h->osc_consumed, n_blocks);
                 count_launch();
             }
-            osc_mix_kernel<<<dim3((n_blocks + 255) / 256, h->n_mix), 256, 0, h->stream>>>(d_out, stride, h->d_mix, h->d_osc,
-                                                                                          h->osc_ring_len, h->osc_consumed, n_blocks);
-            count_launch();
             h->osc_consumed += n_blocks;
-            // top the ring up to a call's worth on the side stream, behind the mix that has just read it
+            // top the ring up to a call's worth on the side stream, behind the kernel that has just read it
+            const int pgrid = (h->n_mix + 31) / 32;
             const int top_up = h->max_blocks - (int)(h->osc_produced - h->osc_consumed);
             if (top_up > 0) {
                 SDRGPU_CUDA(cudaEventRecord(h->ev_mix, h->stream));
                 SDRGPU_CUDA(cudaStreamWaitEvent(h->osc_stream, h->ev_mix, 0));
-                // The chain keeps its scheduler's fma pipe 55 % busy for about a millisecond, and a demodulator warp that
-                // shares the scheduler runs slower while it does.  Round 1 kept other blocks off the producer's SMs by
-                // asking for 220 KB of shared memory it never touched (SDRGPU_OSC_EXCLUSIVE=1 still does); that only worked
-                // for one pipeline per GPU and starves everything else once several tuners share the device, so the
-                // producer is now an ordinary small kernel on its side stream and the cost is reported as measured
-                // (bench.py: with_frequency_corrected_channels).
+                // Round 1 kept other blocks off the producer's SMs by asking for 220 KB of shared memory it never touched
+                // (SDRGPU_OSC_EXCLUSIVE=1 still does); that only worked for one pipeline per GPU and starves everything else
+                // once several tuners share the device, so the producer is an ordinary small kernel on its side stream and
+                // the cost is reported as measured (bench.py: with_frequency_corrected_channels).
                 static const int exclusive = getenv("SDRGPU_OSC_EXCLUSIVE") ? atoi(getenv("SDRGPU_OSC_EXCLUSIVE")) : 0;
                 const int smem = (exclusive && pgrid <= 16) ? 220 * 1024 : 0;
                 if (smem) SDRGPU_CUDA(cudaFuncSetAttribute(osc_produce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

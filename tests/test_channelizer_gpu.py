@@ -277,6 +277,39 @@ def test_frequency_corrected_channels_oscillator_look_ahead_is_bit_exact(gpu):
                 break
 
 
+@pytest.mark.parametrize("m", [400, 800])
+def test_every_bin_frequency_corrected_is_mixed_in_the_channelizer_kernel(gpu, m):
+    """all M bins selected in order as frequency-corrected one-bin channels with one gain: pfb2_kernel multiplies the
+    look-ahead oscillator values in where it stores the rows (no osc_mix_kernel pass).  Every row must equal the oracle's
+    Oscillator + applyGain on the GPU's own uncorrected row, bit for bit, across ragged calls that wrap the rings."""
+    from sdrtrunk_b200.dsp import ComplexPolyphaseChannelizerM2
+    fs = 25000.0 * m
+    rng = np.random.default_rng(29)
+    taps = oracle.sinc_m2_channelizer(25000.0, m, 9)
+    half = m // 2
+    n = half * 900
+    x = sg.interleave(sg.awgn(rng, n, 0.1))
+    offsets = [int(v) for v in rng.integers(-12000, 12000, m)]
+    offsets[3] = 1
+    max_floats = 2 * half * 200
+    plain = ComplexPolyphaseChannelizerM2(taps, int(fs), m, maxInputFloats=max_floats)
+    plain.setChannels(list(range(m)), gain=1.0)
+    corr = ComplexPolyphaseChannelizerM2(taps, int(fs), m, maxInputFloats=max_floats)
+    corr.setOutputChannels([([b], offsets[b], float(m)) for b in range(m)])
+    check = sorted({0, 1, 3, 19, 20, m // 2 - 1, m // 2, m - 2, m - 1} | set(int(v) for v in rng.integers(0, m, 24)))
+    oscs = {b: oracle.Oscillator(offsets[b], 50000.0) for b in check}
+    pos = 0
+    for blocks in [200, 1, 199, 8, 0, 7, 200, 85, 200]:
+        cut = min(x.size, 2 * (pos + half * blocks))
+        rows = plain.receiveChannels(x[2 * pos:cut])
+        got = corr.receiveChannels(x[2 * pos:cut])
+        for b in check:
+            want = oracle.apply_gain(oscs[b].mix(rows[b]), float(m))
+            assert np.array_equal(got[b], want), (pos, b)
+        pos = cut // 2
+    assert pos == n
+
+
 @pytest.mark.parametrize("m", [96, 400, 800])
 @pytest.mark.parametrize("fmt", ["u8", "s8", "s16le"])
 def test_native_tuner_sample_formats(gpu, fmt, m):
