@@ -168,6 +168,44 @@ def test_squelching_fm_matches_oracle(gpu):
         assert np.max(np.abs(got[k] - want)) < 1e-6
 
 
+@pytest.mark.parametrize("rate", [0, 2, 4, 8])
+def test_fused_nbfm_kernel_all_cascade_depths(gpu, rate):
+    """nbfm_fused_kernel with no / one / two / three half-band stages (no decimation: the FIR reads the raw window;
+    decimating: even / odd sample planes, skewed FIR input): 7 channels with different signals, squelch openings and
+    closings, calls that end inside a tile and a FIR length that is not a multiple of 8 -- against the oracle's
+    decimator -> ComplexFIR -> SquelchingFMDemodulator, buffer by buffer."""
+    from sdrtrunk_b200.dsp import Bank
+    rng = np.random.default_rng(40 + rate)
+    d = max(rate, 1)
+    c, block = 7, 1024
+    n = 11 * block                                    # channel-rate input samples per channel (11 assembler buffers)
+    fir = oracle.nbfm_iq_taps() if rate != 4 else oracle.nbfm_iq_taps()[4:-4]     # 45 / 37 taps
+    x = []
+    for k in range(c):
+        loud = sg.nbfm(25000.0 * d, n, audio_hz=300.0 * (k + 1), carrier_offset=150.0 * k, amplitude=0.3) + sg.awgn(rng, n, 1e-3)
+        env = np.ones(n)
+        env[(k * 997) % (n // 2):(k * 997) % (n // 2) + n // 4] = 1e-5          # a quiet stretch somewhere: squelch closes
+        x.append(sg.interleave(loud * env))
+    x = np.stack(x)
+    bank = Bank(c, 25000.0 * d, demod=gpu.DEMOD_FM_SQUELCH, fir_taps=fir, decimation=rate, squelch_alpha=0.01,
+                squelch_threshold_db=-40.0, squelch_ramp=4, block_size=block, max_samples_per_call=8 * block)
+    cuts = [0, 3 * block, 4 * block, 9 * block, 11 * block]       # calls of 3, 1, 5 and 2 buffers
+    got = np.concatenate([bank.process(x[:, 2 * a:2 * b]) for a, b in zip(cuts[:-1], cuts[1:])], axis=1)
+    assert got.shape == (c, n // d)
+    for k in range(c):
+        dec = oracle.Decimator(rate) if rate else None
+        f, fm = oracle.ComplexFIR(fir), oracle.SquelchingFMDemodulator(0.01, -40.0, 4)
+        want = []
+        for b in range(n // block):
+            buf = x[k, 2 * block * b:2 * block * (b + 1)]
+            want.append(fm.demodulate(f.filter(dec.decimate_complex(buf) if dec else buf)))
+        want = np.concatenate(want)
+        assert np.array_equal(got[k] == 0.0, want == 0.0), (rate, k)       # identical gating
+        assert np.any(want != 0.0) and np.any(want == 0.0)
+        assert np.max(np.abs(got[k] - want)) < 1e-6, (rate, k)
+        assert np.mean(got[k] == want) > 0.999
+
+
 # ------------------------------------------------------------------------------------------------ DQPSK
 def _p25_signal(kind, rng, n, k):
     rate = 6000.0 if kind == "hdqpsk" else 4800.0

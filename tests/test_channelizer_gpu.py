@@ -374,28 +374,39 @@ def test_airspy_sample_converter_bit_exact(gpu, packed):
 
 
 def test_airspy_late_merging_segments_are_repaired(gpu):
-    """A slow, noiseless square wave: guessed and true averages can need more than the 4 096-sample warm-up to become
-    bit-identical.  Such segments are redone in parallel from their predecessor's end; the result must be the Java's and
-    the sequential fallback must not be needed."""
+    """A slow, noiseless square wave: on its flat stretches the float recursion stalls next to its fixed point and the
+    guessed and true averages of whole runs of segments never become bit-identical.  The repair walk redoes each run
+    from the true value in front of it (runs in parallel); the result must be the Java's and the sequential fallback
+    must not be needed."""
     from sdrtrunk_b200.dsp import AirspySampleConverter
     n = 40 * 2048
     t = np.arange(n)
     x = 300.0 / 2048 * np.sign(np.sin(t * 0.001)) + 5.0 / 2048
-    raw = sg.airspy_raw(x)
-    ref, conv = oracle.AirspySampleConverter(), AirspySampleConverter(maxSamples=1 << 17)
-    for _ in range(3):
-        assert np.array_equal(conv.convert(raw), ref.convert(raw))
-    assert conv.mismatches() == 0
+    for packed in (False, True):
+        raw = sg.airspy_raw(x, packed)
+        ref, conv = oracle.AirspySampleConverter(), AirspySampleConverter(maxSamples=1 << 17)
+        ref.setSamplePacking(packed)
+        conv.setSamplePacking(packed)
+        for _ in range(3):
+            assert np.array_equal(conv.convert(raw), ref.convert(raw))
+        assert conv.mismatches() == 0
+        assert conv.repaired() > 0
 
 
-def test_airspy_speculation_fallback_is_exact(gpu):
-    """A pathological stream defeats the speculation: with constant samples the recursion stalls half an ulp short of
-    its fixed point, on the side it came from.  The true average comes down from 0.9 and stalls just above 0.75; a
-    segment that guesses 0 stalls just below and never meets it.  The verification must notice and the sequential
-    fallback must still give the Java's result."""
+@pytest.mark.parametrize("walk", [True, False])
+def test_airspy_speculation_fallback_is_exact(gpu, monkeypatch, walk):
+    """A pathological stream defeats the speculation altogether: with constant samples the recursion stalls half an ulp
+    short of its fixed point, on the side it came from.  The true average comes down from 0.9 and stalls just above
+    0.75; the guesses stall elsewhere, segments agree and disagree with their neighbours at random and no repair walk
+    starts from a true value except the first, which runs into the next one.  The verification must notice (every start
+    against its predecessor's end) and the sequential fallback of the commit step must still give the Java's result --
+    with the repair walk and without it (SDRGPU_AIRSPY_WALK=0)."""
     from sdrtrunk_b200.dsp import AirspySampleConverter
+    if not walk:
+        monkeypatch.setenv("SDRGPU_AIRSPY_WALK", "0")
     n = 4 * 4096 + 512
     ref, conv = oracle.AirspySampleConverter(), AirspySampleConverter(maxSamples=1 << 16)
+    monkeypatch.delenv("SDRGPU_AIRSPY_WALK", raising=False)
     high, flat = sg.airspy_raw(np.full(n, 0.9)), sg.airspy_raw(np.full(n, 0.75))
     assert np.array_equal(conv.convert(high), ref.convert(high))
     for _ in range(3):
