@@ -73,6 +73,7 @@ struct ChanParams {
     int osc_ring_len, osc_start;
     float2 *next_state;  // pfb2_kernel only: one CTA also writes the next call's history (else save_state_kernel)
     int next_len, consumed;
+    float neg_zero;      // -0.0f as a run-time value: the addend of the filter bank's packed products (fb_thread)
 };
 
 // ByteSampleConverter / SignedByteSampleConverter (J/source/tuner/... lookup tables: (b - 127) / 128.0f, b / 128.0f): both
@@ -337,6 +338,12 @@ __device__ __forceinline__ void fb_thread(const ChanParams &p, const float2 *__r
         hB[t] = __ldg(p.taps + n + half + t * M);
     }
     float2 accA[NB], accB[NB];
+    // The Java rounds the product and the sum separately (no Math.fma in the filter bank).  The I and Q rails share packed
+    // instructions: the product is an FFMA2 whose addend is -0.0 (x h + -0 is the rounded product, signed zeros included),
+    // the sum an FADD2 -- two instructions where four scalar ones were.  The -0.0 is a kernel parameter on purpose: ptxas
+    // contracts mul.rn.f32x2 + add.rn.f32x2, and an FFMA2 with a literal -0.0 addend + add, into ONE FFMA2 whatever -fmad
+    // says (checked in the SASS; round 1 gave the packed filter bank up for that reason).
+    const float2 nz = make_float2(p.neg_zero, p.neg_zero);
 #pragma unroll
     for (int pp = NB - 1; pp >= -(2 * TT - 1); --pp) {
         const float2 x = !FAST ? load_x<RAW>(p, b0 + pp, r)
@@ -349,10 +356,10 @@ __device__ __forceinline__ void fb_thread(const ChanParams &p, const float2 *__r
                 if (t == 0) accA[bl] = make_float2(__fmul_rn(x.x, hA[t]), __fmul_rn(x.y, hA[t]));
                 else accA[bl] = make_float2(__fmaf_rn(x.x, hA[t], accA[bl].x), __fmaf_rn(x.y, hA[t], accA[bl].y));
 #else
-                const float px = __fmul_rn(x.x, hA[t]), py = __fmul_rn(x.y, hA[t]);
+                const float2 pr = __ffma2_rn(x, make_float2(hA[t], hA[t]), nz);
                 // (the Java's 0.0f + product differs from the product only in the sign of a zero)
-                if (t == 0) accA[bl] = make_float2(px, py);
-                else accA[bl] = make_float2(__fadd_rn(accA[bl].x, px), __fadd_rn(accA[bl].y, py));
+                if (t == 0) accA[bl] = pr;
+                else accA[bl] = __fadd2_rn(accA[bl], pr);
 #endif
             }
             const int bm = pp + 1 + 2 * t;  // branch n + M/2: unit P = B - 1 - 2t
@@ -361,9 +368,9 @@ __device__ __forceinline__ void fb_thread(const ChanParams &p, const float2 *__r
                 if (t == 0) accB[bm] = make_float2(__fmul_rn(x.x, hB[t]), __fmul_rn(x.y, hB[t]));
                 else accB[bm] = make_float2(__fmaf_rn(x.x, hB[t], accB[bm].x), __fmaf_rn(x.y, hB[t], accB[bm].y));
 #else
-                const float px = __fmul_rn(x.x, hB[t]), py = __fmul_rn(x.y, hB[t]);
-                if (t == 0) accB[bm] = make_float2(px, py);
-                else accB[bm] = make_float2(__fadd_rn(accB[bm].x, px), __fadd_rn(accB[bm].y, py));
+                const float2 pr = __ffma2_rn(x, make_float2(hB[t], hB[t]), nz);
+                if (t == 0) accB[bm] = pr;
+                else accB[bm] = __fadd2_rn(accB[bm], pr);
 #endif
             }
         }
@@ -489,9 +496,8 @@ __global__ void __launch_bounds__(NT, MINB) pfb2_kernel(const ChanParams p)
                 } else {
 #pragma unroll
                     for (int k2 = 0; k2 < R2; k2++) {
-                        float2 v = a[k2];
-                        v.x = __fmul_rn(__fmul_rn(v.x, inv), g);
-                        v.y = __fmul_rn(__fmul_rn(v.y, inv), g);
+                        // (1 / M, then the gain: two packed multiplies for four scalar ones)
+                        const float2 v = __fmul2_rn(__fmul2_rn(a[k2], make_float2(inv, inv)), make_float2(g, g));
                         *reinterpret_cast<float2 *>(o) = v;
                         o += ostep;
                     }
@@ -1078,6 +1084,7 @@ sdrgpu_status sdrgpu::chan_enqueue(sdrgpu_channelizer *h, const float2 *d_in, in
     if (n_blocks > 0) {
         if (fused_mix) SDRGPU_TRY(ensure_osc());
         ChanParams p{};
+        p.neg_zero = -0.0f;
         p.state = state;
         p.in = d_in;
         p.raw = fuse_convert ? raw : nullptr;

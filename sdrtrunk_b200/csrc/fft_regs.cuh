@@ -9,9 +9,18 @@
 
 namespace rfft {
 
+// complex add / subtract as ONE packed instruction (sm_100 add.rn.f32x2: both rails correctly rounded, i.e. the same bits as
+// two scalar adds; the subtraction's negation folds into the FADD2 operand)
+#ifndef SDRGPU_FFT_SCALAR
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+#else
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+#endif
 __device__ __forceinline__ float2 jmul(float2 a) { return make_float2(-a.y, a.x); }   // * (+j)
+// (packed: a.y (-wi, wr), then a.x (wr, wi) + that = two FFMA2 for 2 FMUL + 2 FFMA -- tried: the twiddle pairs are no longer
+// 32-bit immediates but 64-bit operands fetched by LDC.64 / MOV pairs, and the kernel grew from 3592 to 3648 instructions)
 __device__ __forceinline__ float2 cmul(float2 a, float wr, float wi)
 {
     return make_float2(fmaf(a.x, wr, -a.y * wi), fmaf(a.x, wi, a.y * wr));
