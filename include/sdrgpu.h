@@ -57,8 +57,11 @@ uint64_t sdrgpu_launch_count(void);
  *   FIR_CTAS_PER_SM / PFB_CTAS_PER_SM: resident CTAs per SM of fir_agc_kernel / pfb2_kernel while a pipeline runs its
  *   time chunks concurrently with the symbol demodulator (0 = whatever fits).  The demodulator is bound by the latency of
  *   its per-symbol feedback chain; every other resident warp on its scheduler delays each of its dependent instructions,
- *   so the filter kernels that overlap it are held to a few warps per scheduler. */
-enum { SDRGPU_TUNE_FIR_CTAS_PER_SM = 0, SDRGPU_TUNE_PFB_CTAS_PER_SM = 1, SDRGPU_TUNE_THROTTLE_ALWAYS = 2, SDRGPU_TUNE_COUNT = 8 };
+ *   so the filter kernels that overlap it are held to a few warps per scheduler.
+ *   FIR_TILES_PER_CTA: consecutive assembler buffers of a channel one CTA of the FIR kernels filters (0 = chosen from the
+ *   bank size: up to 4 while the grid still fills the GPU a dozen times over). */
+enum { SDRGPU_TUNE_FIR_CTAS_PER_SM = 0, SDRGPU_TUNE_PFB_CTAS_PER_SM = 1, SDRGPU_TUNE_THROTTLE_ALWAYS = 2,
+       SDRGPU_TUNE_FIR_TILES_PER_CTA = 3, SDRGPU_TUNE_COUNT = 8 };
 sdrgpu_status sdrgpu_set_tuning(int knob, int value);
 int sdrgpu_get_tuning(int knob);
 

@@ -17,6 +17,7 @@ WINDOW_HAMMING, WINDOW_BLACKMAN = 0, 1
 DEMOD_NONE, DEMOD_FM, DEMOD_FM_SQUELCH, DEMOD_DQPSK_DECISION, DEMOD_DQPSK_GARDNER = 0, 1, 2, 3, 4
 FORMAT_F32, FORMAT_U8, FORMAT_S8, FORMAT_S16LE, FORMAT_AIRSPY_U16LE, FORMAT_AIRSPY_PACKED12 = 0, 1, 2, 3, 4, 5
 PRESET_P25_C4FM, PRESET_P25_LSM, PRESET_P25_HDQPSK, PRESET_NBFM, PRESET_DMR = 0, 1, 2, 3, 4
+TUNE_FIR_CTAS_PER_SM, TUNE_PFB_CTAS_PER_SM, TUNE_THROTTLE_ALWAYS, TUNE_FIR_TILES_PER_CTA = 0, 1, 2, 3
 SYNC_NONE, SYNC_P25_PHASE1, SYNC_P25_PHASE2, SYNC_P25_PHASE2_FRAMED = 0, 1, 2, 3
 P2_EVENT_FRAGMENT, P2_EVENT_SYNC_LOSS, P2_EVENT_INVERSION, P2_EVENT_SYNCHRONIZED = 1, 2, 4, 32
 (SYNC_EVENT_NONE, SYNC_EVENT_SYNC, SYNC_EVENT_INVERSION_90_CW, SYNC_EVENT_INVERSION_90_CCW, SYNC_EVENT_INVERSION_180,

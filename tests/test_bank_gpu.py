@@ -94,6 +94,40 @@ def test_agc_block_bit_exact(gpu):
         assert np.array_equal(got[k], want), k
 
 
+@pytest.mark.parametrize("n_taps", [5, 8, 24, 72, 154, 301])
+def test_fir_agc_whole_buffers_bit_exact(gpu, n_taps):
+    """FIR + block AGC over whole 1024-sample assembler buffers -- the decoders' framing, served by
+    fir_agc_split_kernel (per-warp windows, split-phase maximum exchange) -- in calls of 1, 7, 2, 4 and 3 buffers
+    (odd and even tile counts per CTA), with ragged calls in between that the general fir_agc_kernel takes: the
+    history a kernel leaves is the history the other one starts from"""
+    from sdrtrunk_b200 import native
+    from sdrtrunk_b200.dsp import Bank
+    rng = np.random.default_rng(100 + n_taps)
+    taps = (rng.standard_normal(n_taps) / n_taps).astype(np.float32)
+    c = 7
+    steps = (1024, 7 * 1024, 1000, 24, 2 * 1024, 4 * 1024, 500, 524, 3 * 1024)
+    n = sum(steps)
+    x = _noise(rng, c, n, 0.05)
+    x[1, 2 * 3000:2 * 6000] = 0.0     # silent buffers: the gain clamps at 1 / 1e-4
+    x[2] *= 1e-6
+    bank = Bank(c, 50000.0, fir_taps=taps, fir_gain=1.25, agc=True, max_samples_per_call=8 * 1024)
+    # a small bank would get one buffer per CTA: ask for the large banks' launch shape (3 consecutive buffers per CTA)
+    native.check(native.lib().sdrgpu_set_tuning(native.TUNE_FIR_TILES_PER_CTA, 3))
+    try:
+        parts, pos = [], 0
+        for step in steps:
+            parts.append(bank.process(x[:, 2 * pos:2 * (pos + step)]))
+            pos += step
+    finally:
+        native.check(native.lib().sdrgpu_set_tuning(native.TUNE_FIR_TILES_PER_CTA, 0))
+    got = np.concatenate(parts, axis=1)
+    assert got.shape == (c, 2 * n)
+    for k in range(c):
+        y = oracle.ComplexFIR(taps, 1.25).filter(x[k])
+        want = np.concatenate([oracle.agc_block(y[2048 * b:2048 * (b + 1)]) for b in range(n // 1024)])
+        assert np.array_equal(got[k], want), k
+
+
 def test_single_channel_drop_in_classes(gpu):
     from sdrtrunk_b200 import native
     from sdrtrunk_b200.dsp import (ComplexFeedForwardGainControl, ComplexFIRFilter2, DecimationFilterFactory,
