@@ -770,17 +770,17 @@ def roofline_tuner(w, r, peak, peak_src, steps):
     chain_flop = chain_flop_per_input_sample(w.m, n_fir) * w.total_complex
     ach = chain_flop / (r["ms_per_step"] * 1e-3) / 1e12
     table = [pfb,
-             {"kernel": "fir_agc_kernel", "bound": "fp32", "ms": k["fir_agc"], "launches_per_step": 1,
+             {"kernel": "fir_agc_split_kernel", "bound": "fp32", "ms": k["fir_agc"], "launches_per_step": 1,
               "achieved": fir_flop / (k["fir_agc"] * 1e-3) / 1e12, "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s",
               "frac": fir_flop / (k["fir_agc"] * 1e-3) / 1e12 / FP32_PEAK_TFLOPS, "algorithmic_flop_per_step": fir_flop},
-             {"kernel": "psk_kernel", "bound": "latency (serial per-symbol feedback loop); fp32 view", "ms": k["psk"],
+             {"kernel": "psk_multi_kernel", "bound": "latency (serial per-symbol feedback loop); fp32 view", "ms": k["psk"],
               "launches_per_step": 1, "achieved": psk_flop / (k["psk"] * 1e-3) / 1e12, "peak": FP32_PEAK_TFLOPS,
               "unit": "TFLOP/s", "frac": psk_flop / (k["psk"] * 1e-3) / 1e12 / FP32_PEAK_TFLOPS,
               "algorithmic_flop_per_step": psk_flop,
               "channels_in_launch": w.T * w.m}]
     return {"bound": "fp32", "achieved": ach, "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": ach / FP32_PEAK_TFLOPS,
             "traffic": load_traffic("chain_%s_t%d" % (w.name, w.T)),
-            "kernel": "chain: pfb2_kernel x %d + fir_agc_kernel + psk_kernel (whole step; the demodulator overlaps the "
+            "kernel": "chain: pfb2_kernel x %d + fir_agc_split_kernel + psk_multi_kernel (whole step; the demodulator overlaps the "
                       "filters of the next time chunk)" % w.T,
             "kernel_ms": r["ms_per_step"], "algorithmic_flop_per_input_sample": chain_flop_per_input_sample(w.m, n_fir),
             "algorithmic_flop_per_step": chain_flop, "peak_source": "148 SM x 128 FFMA lanes x 2 x 1.965 GHz (SURVEY.md 8d)",
@@ -897,13 +897,13 @@ def run_bank(name, args, rank, world, local_rank, torch, dist, as_secondary=Fals
         flop = channels * n * (4.0 * 154 + 40.0)
         ach = flop / (ms_step * 1e-3) / 1e12
         roof = {"bound": "fp32", "achieved": ach, "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": ach / FP32_PEAK_TFLOPS,
-                "traffic": load_traffic(name), "kernel": "chain: fir_agc_kernel + psk_kernel<gardner> (whole step)",
+                "traffic": load_traffic(name), "kernel": "chain: fir_agc_split_kernel + psk_multi_kernel<gardner> (whole step)",
                 "kernel_ms": ms_step, "algorithmic_flop_per_step": flop,
                 "peak_source": "148 SM x 128 FFMA lanes x 2 x 1.965 GHz (SURVEY.md 8d)",
-                "kernels": [{"kernel": "fir_agc_kernel", "bound": "fp32", "ms": k_filter,
+                "kernels": [{"kernel": "fir_agc_split_kernel", "bound": "fp32", "ms": k_filter,
                              "achieved": channels * n * 616.0 / (k_filter * 1e-3) / 1e12, "peak": FP32_PEAK_TFLOPS,
                              "unit": "TFLOP/s", "frac": channels * n * 616.0 / (k_filter * 1e-3) / 1e12 / FP32_PEAK_TFLOPS},
-                            {"kernel": "psk_kernel<gardner>", "bound": "latency (serial per-symbol feedback loop)",
+                            {"kernel": "psk_multi_kernel<gardner>", "bound": "latency (serial per-symbol feedback loop)",
                              "ms": k_demod, "channels_in_launch": channels}]}
     else:
         alg = channels * n * (8.0 + 2.0)       # 8 B in + 4 B out per decimated-by-2 sample

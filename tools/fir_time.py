@@ -19,6 +19,8 @@ def main():
     rng = np.random.default_rng(0)
     n = 12 * 1024
     fir = oracle_taps()
+    if os.environ.get("FIR_TILES_PER_CTA"):   # launch shape: consecutive buffers per CTA (sdrgpu_set_tuning)
+        native.check(native.lib().sdrgpu_set_tuning(native.TUNE_FIR_TILES_PER_CTA, int(os.environ["FIR_TILES_PER_CTA"])))
     for c in [int(a) for a in sys.argv[1:]] or [800, 6400]:
         x = rng.standard_normal((c, 2 * n), dtype=np.float32) * 0.1
         bank = Bank.preset(native.PRESET_P25_C4FM, c, 50000.0, fir, max_samples_per_call=n)
@@ -28,7 +30,8 @@ def main():
             bank.process(x)
             best = min(best, bank.lastKernelMs()[0])
         bank.dispose()
-        print("%5d channels x %d samples: filter stage %.4f ms (SDRGPU_FIR_SPLIT=%s)" % (c, n, best, os.environ.get("SDRGPU_FIR_SPLIT", "1")),
+        print("%5d channels x %d samples: filter stage %.4f ms (SDRGPU_FIR_SPLIT=%s, FIR_TILES_PER_CTA=%s)" %
+              (c, n, best, os.environ.get("SDRGPU_FIR_SPLIT", "1"), os.environ.get("FIR_TILES_PER_CTA", "auto")),
               flush=True)
 
 
