@@ -596,6 +596,31 @@ class TunerWorkload:
                                                     C.c_void_p(self.sym_host.data_ptr()), self.sym_stride, None, 0,
                                                     C.c_void_p(self.cnt_host.data_ptr()), n.HOST))
 
+    def step_host_stream(self):
+        """the host-buffer step as a continuous stream delivers it: sdrgpu_pipeline_submit_multi with two calls in flight
+        (the H2D copies of step k + 1 overlap the kernels of step k), alternating pinned output buffers; every step still
+        copies its whole input in and its dibits + counts out"""
+        n, L = self.native, self.L
+        _, ptrs = self.host_inputs(self.fmt)
+        if not hasattr(self, "_stream_out"):
+            torch = self.torch
+            self._stream_out = [(self.sym_host, self.cnt_host),
+                                (torch.zeros_like(self.sym_host).pin_memory(), torch.zeros_like(self.cnt_host).pin_memory())]
+            self._stream_k, self._stream_inflight = 0, 0
+        sym, cnt = self._stream_out[self._stream_k & 1]
+        n.check(L.sdrgpu_pipeline_submit_multi(self.pipeline._h, ptrs, self.n_floats, C.c_void_p(sym.data_ptr()),
+                                               self.sym_stride, C.c_void_p(cnt.data_ptr())))
+        self._stream_k += 1
+        self._stream_inflight += 1
+        if self._stream_inflight == 2:
+            n.check(L.sdrgpu_pipeline_wait(self.pipeline._h))
+            self._stream_inflight -= 1
+
+    def stream_drain(self):
+        while getattr(self, "_stream_inflight", 0) > 0:
+            self.native.check(self.L.sdrgpu_pipeline_wait(self.pipeline._h))
+            self._stream_inflight -= 1
+
     def sanity(self):
         """decoded-vs-transmitted dibits of a few rows (first pass over the streams, from the reset state; a plausibility
         figure for the timed workload -- parity itself is tests/)"""
@@ -670,12 +695,29 @@ def measure_tuner(w, args, world, timed, full=True):
         return {"value": total / (per * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": w.T * w.n_floats * w.bytes_per_value(fmt),
                 "d2h_bytes_per_step": w.d2h, "ms_per_step": per, "input": note}
 
+    def e2e_stream_leg(fmt, note):
+        # K steps with two calls in flight; the timed region ends with a full device synchronise (wall clock), which is
+        # when the last step's dibits are on the host
+        w.set_format(fmt)
+        w.host_inputs(fmt)
+        ms, wall = timed(w.step_host_stream, w.stream, steps, max(3, args.warmup))
+        w.stream_drain()
+        per = max(ms, wall) / steps
+        return {"value": total / (per * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": w.T * w.n_floats * w.bytes_per_value(fmt),
+                "d2h_bytes_per_step": w.d2h, "ms_per_step": per, "input": note}
+
     if not args.device_only:
         if w.pipeline is not None:
             # the chain's host-buffer path takes what a 20 MS/s USB tuner delivers: signed 8-bit I/Q (HackRF;
             # SignedByteSampleConverter), converted on the device in front of the channelizer
-            res["e2e"] = e2e_leg("s8", "tuner-native signed 8-bit I/Q in pinned host buffers (SignedByteSampleConverter "
-                                       "format, converted on the device), dibits + counts back to pinned host buffers")
+            blocking = e2e_leg("s8", "tuner-native signed 8-bit I/Q in pinned host buffers (SignedByteSampleConverter "
+                                     "format, converted on the device), dibits + counts back to pinned host buffers; one "
+                                     "blocking sdrgpu_pipeline_process_multi call per step")
+            res["e2e"] = e2e_stream_leg("s8", "tuner-native signed 8-bit I/Q in pinned host buffers (SignedByteSampleConverter "
+                                              "format, converted on the device), dibits + counts back to pinned host buffers; "
+                                              "a continuous stream: sdrgpu_pipeline_submit_multi / _wait with two steps in "
+                                              "flight, every step's H2D and D2H copies inside the timed region")
+            res["e2e"]["blocking_call"] = {"value": blocking["value"], "unit": UNIT, "ms_per_step": blocking["ms_per_step"]}
             if full and w.T == 1:
                 res["e2e_f32_input"] = e2e_leg("f32", "float32 I/Q in pinned host buffers (the reference's float[] buffers)")
         else:

@@ -362,6 +362,18 @@ sdrgpu_status sdrgpu_pipeline_create_multi(sdrgpu_pipeline **p, sdrgpu_channeliz
 sdrgpu_status sdrgpu_pipeline_process_multi(sdrgpu_pipeline *p, const void *const *iq, int n_floats, int in_mem,
                                             uint8_t *symbols, int symbol_stride, float *demod,
                                             long long demod_stride_floats, int *counts, int out_mem);
+/* Asynchronous form for a continuous stream (host buffers in, dibits out; DQPSK banks).  A synchronous call cannot hide
+ * its first H2D chunk nor the chain of its last one; a tuner delivers buffer after buffer (the reference's 5 ms cadence,
+ * J/dsp/filter/channelizer/PolyphaseChannelManager.java:582-623), so the copies of buffer k + 1 can run while the kernels
+ * of buffer k finish.  submit enqueues the call and returns; the caller must leave iq[...], symbols and counts alone until
+ * the matching sdrgpu_pipeline_wait returns (the one documented exception to "the library never keeps a caller pointer").
+ * At most two calls in flight (BAD_STATE beyond): submit(k + 1), then wait() -- which returns when the OLDEST call in
+ * flight, k, has its outputs on the host -- with two alternating sets of host buffers.  Results are those of the same
+ * sequence of sdrgpu_pipeline_process_multi calls.  wait with nothing in flight returns at once; process / process_multi
+ * refuse to run while calls are in flight. */
+sdrgpu_status sdrgpu_pipeline_submit_multi(sdrgpu_pipeline *p, const void *const *iq, int n_floats, uint8_t *symbols,
+                                           int symbol_stride, int *counts);
+sdrgpu_status sdrgpu_pipeline_wait(sdrgpu_pipeline *p);
 /* time chunks for device-resident input (default 1: nothing to copy, but with many channels the latency-bound
  * demodulator of chunk i overlaps the issue-bound channelizer / FIR kernels of chunk i+1) */
 sdrgpu_status sdrgpu_pipeline_set_device_chunks(sdrgpu_pipeline *p, int chunks);

@@ -26,6 +26,7 @@
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <utility>
 #include <vector>
 
 #include "common.cuh"
@@ -834,6 +835,8 @@ struct sdrgpu_channelizer {
     int cur_state = 0;
     float2 *d_in = nullptr;    // staging for host input (float I/Q)
     uint8_t *d_raw = nullptr;  // staging for host input in a native tuner format
+    float2 *d_in_alt = nullptr;    // the other staging pair of an asynchronous pipeline (chan_swap_staging): the H2D copies of
+    uint8_t *d_raw_alt = nullptr;  // call k + 1 land while the kernels of call k still read theirs
     int in_format = SDRGPU_FORMAT_F32;
     sdrgpu_airspy *airspy = nullptr;   // SDRGPU_FORMAT_AIRSPY_*: the stateful raw-sample converter
     float *d_out = nullptr;    // staging for host output
@@ -1258,6 +1261,16 @@ const float2 *sdrgpu::chan_convert(sdrgpu_channelizer *h, const void *iq_device,
     }
     return h->d_in + first;
 }
+void sdrgpu::chan_swap_staging(sdrgpu_channelizer *h)
+{
+    std::swap(h->d_in, h->d_in_alt);
+    std::swap(h->d_raw, h->d_raw_alt);
+}
+// where chan_upload puts a host buffer: device-resident input in the handle's sample format
+const void *sdrgpu::chan_staging(const sdrgpu_channelizer *h)
+{
+    return h->in_format == SDRGPU_FORMAT_F32 ? static_cast<const void *>(h->d_in) : static_cast<const void *>(h->d_raw);
+}
 void sdrgpu::chan_set_throttled(sdrgpu_channelizer *h, bool on) { h->throttled = on; }
 int sdrgpu::chan_half(const sdrgpu_channelizer *h) { return h->half; }
 int sdrgpu::chan_max_in(const sdrgpu_channelizer *h) { return h->max_in_complex; }
@@ -1391,6 +1404,8 @@ sdrgpu_status sdrgpu_chan_destroy(sdrgpu_channelizer *h)
     cudaFree(h->d_state[1]);
     cudaFree(h->d_in);
     cudaFree(h->d_raw);
+    cudaFree(h->d_in_alt);
+    cudaFree(h->d_raw_alt);
     sdrgpu::airspy_destroy(h->airspy);
     cudaFree(h->d_out);
     cudaFree(h->d_sel);

@@ -65,6 +65,8 @@ sdrgpu_status chan_upload(sdrgpu_channelizer *h, const void *iq, size_t first, i
 const float2 *chan_convert(sdrgpu_channelizer *h, const void *iq_device_or_null, size_t first, int n);
 size_t chan_complex_bytes(const sdrgpu_channelizer *h);   // bytes of one complex sample in the handle's input format
 int chan_half(const sdrgpu_channelizer *h);
+void chan_swap_staging(sdrgpu_channelizer *h);   // host-input staging buffers alternate between the calls of an asynchronous pipeline
+const void *chan_staging(const sdrgpu_channelizer *h);
 void chan_set_throttled(sdrgpu_channelizer *h, bool on);   // next launches share the GPU with the demodulator (SDRGPU_TUNE_PFB_CTAS_PER_SM)
 int chan_max_in(const sdrgpu_channelizer *h);
 int chan_leftover(const sdrgpu_channelizer *h);  // samples buffered that did not fill a block yet (mSampleBufferPointer)   // complex samples one process call may carry (max_input_floats / 2)

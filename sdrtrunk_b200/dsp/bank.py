@@ -253,6 +253,40 @@ class Pipeline:
                                                      dem.shape[1], native.ptr(counts), native.HOST))
         return dem[:, :width]
 
+    def submit(self, samples):
+        """asynchronous process() for a continuous stream of host buffers (DQPSK banks): enqueues the call and returns;
+        wait() then returns the per-channel dibit arrays of the OLDEST call in flight.  At most two calls in flight
+        (sdrgpu_pipeline_submit_multi / sdrgpu_pipeline_wait); the buffers are kept alive here until their wait()."""
+        L = native.lib()
+        bank = self.bank
+        assert bank.is_dqpsk
+        multi = len(self.channelizers) > 1
+        bufs = list(samples) if multi else [samples]
+        assert len(bufs) == len(self.channelizers)
+        bufs = [np.ascontiguousarray(b, dtype=getattr(self.channelizer, "_dtype", np.float32)) for b in bufs]
+        n_floats = bufs[0].size // 3 * 2 if getattr(self.channelizer, "_packed", False) else bufs[0].size
+        assert all(b.size == bufs[0].size for b in bufs)
+        in_ptrs = (C.c_void_p * len(bufs))(*[C.cast(native.ptr(b), C.c_void_p) for b in bufs])
+        n = self.channelizer.blocksFor(n_floats)
+        blocks = (self._pending + n) // bank.block_size
+        n_out = blocks * (bank.block_size // max(bank.decimation, 1))
+        stride = max(16, n_out // 3 + 16)
+        symbols = np.zeros((bank.n_channels, stride), np.uint8)
+        counts = np.zeros(bank.n_channels, np.int32)
+        native.check(L.sdrgpu_pipeline_submit_multi(self._h, in_ptrs, n_floats, native.ptr(symbols), stride, native.ptr(counts)))
+        self._pending = (self._pending + n) % bank.block_size
+        if not hasattr(self, "_in_flight"):
+            self._in_flight = []
+        self._in_flight.append((bufs, in_ptrs, symbols, counts))
+
+    def wait(self):
+        """results of the oldest submitted call (None if nothing is in flight)"""
+        if not getattr(self, "_in_flight", None):
+            return None
+        native.check(native.lib().sdrgpu_pipeline_wait(self._h))
+        _, _, symbols, counts = self._in_flight.pop(0)
+        return [symbols[c, :counts[c]].copy() for c in range(self.bank.n_channels)]
+
     def dispose(self):
         if getattr(self, "_h", None) is not None and self._h:
             native.lib().sdrgpu_pipeline_destroy(self._h)

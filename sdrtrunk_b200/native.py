@@ -131,6 +131,8 @@ PROTOTYPES = {
     "sdrgpu_pipeline_set_device_chunks": (C.c_int, [_vp, C.c_int]),
     "sdrgpu_pipeline_create_multi": (C.c_int, [_vpp, _vp, C.c_int, _vp]),
     "sdrgpu_pipeline_process_multi": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, C.c_int, _vp, C.c_longlong, _vp, C.c_int]),
+    "sdrgpu_pipeline_submit_multi": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, _vp]),
+    "sdrgpu_pipeline_wait": (C.c_int, [_vp]),
     "sdrgpu_pipeline_destroy": (C.c_int, [_vp]),
     "sdrgpu_pipeline_process": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, C.c_int, _vp, C.c_longlong, _vp, C.c_int]),
 }

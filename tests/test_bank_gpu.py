@@ -949,6 +949,68 @@ def test_multi_tuner_pipeline_equals_single_tuner_pipelines(gpu, fmt):
             assert np.array_equal(got[r], want[r]), (kw, r)
 
 
+@pytest.mark.parametrize("fmt", ["f32", "s8"])
+def test_asynchronous_pipeline_calls_equal_the_synchronous_sequence(gpu, fmt):
+    """sdrgpu_pipeline_submit_multi / sdrgpu_pipeline_wait: a stream of host buffers with two calls in flight (the H2D
+    copies of call k + 1 overlap the kernels of call k; alternating staging buffers) gives every channel the dibits of
+    the same buffers through synchronous calls -- calls long enough to be cut into chunks (left in flight), one too
+    short for that (runs to completion inside submit), an empty one; then a synchronous call continues the stream."""
+    from sdrtrunk_b200.dsp import Bank, ComplexPolyphaseChannelizerM2, Pipeline
+    m, n_ch = 96, 40 * 1024
+    rng = np.random.default_rng(91)
+    bins = [[2, 30, 77], [5, 6, 95]]
+    xs = [_tuner_stream(rng, m, n_ch, b) for b in bins]
+    if fmt == "s8":
+        xs = [np.clip(np.round(x * 128.0 * 4), -128, 127).astype(np.int8) for x in xs]
+    taps, fir = oracle.sinc_m2_channelizer(25000.0, m, 9), c4fm_taps()
+    rows = sum(len(b) for b in bins)
+    unit = m * 1024          # input values per assembler buffer of every channel
+    sizes = [9 * unit, 11 * unit + 4000, 0, 1 * unit, 8 * unit, 6 * unit]
+    sizes.append(xs[0].size - sum(sizes))
+    assert sizes[-1] > 3 * unit
+    edges = np.cumsum([0] + sizes)
+
+    def pipeline():
+        chans = []
+        for k in range(2):
+            ch = ComplexPolyphaseChannelizerM2(taps, 2400000, m, maxInputFloats=12 * unit)
+            ch.setChannels(bins[k])
+            ch.setSampleFormat(fmt)
+            chans.append(ch)
+        pipe = Pipeline(chans, Bank.preset(gpu.PRESET_P25_C4FM, rows, 50000.0, fir, max_samples_per_call=12 * 1024))
+        pipe.setChunks(4)
+        return pipe
+
+    sync = pipeline()
+    want = [sync.process([x[a:b] for x in xs]) for a, b in zip(edges[:-1], edges[1:])]
+    assert sum(w.size for w in want[0]) > 1000
+
+    pipe = pipeline()
+    got = []
+    for i, (a, b) in enumerate(zip(edges[:-2], edges[1:-1])):
+        pipe.submit([x[a:b].copy() for x in xs])
+        if i >= 1:
+            got.append(pipe.wait())          # two in flight, then the oldest comes back
+    got.append(pipe.wait())
+    assert pipe.wait() is None
+    got.append(pipe.process([x[edges[-2]:edges[-1]] for x in xs]))   # a synchronous call carries on from there
+    assert len(got) == len(want)
+    for i in range(len(want)):
+        for r in range(rows):
+            assert np.array_equal(got[i][r], want[i][r]), (i, r)
+
+    # three submits without a wait, and a synchronous call with calls in flight, are refused
+    pipe2 = pipeline()
+    pipe2.submit([x[:9 * unit] for x in xs])
+    pipe2.submit([x[9 * unit:18 * unit] for x in xs])
+    with pytest.raises(gpu.IllegalStateException):
+        pipe2.submit([x[18 * unit:27 * unit] for x in xs])
+    with pytest.raises(gpu.IllegalStateException):
+        pipe2.process([x[18 * unit:27 * unit] for x in xs])
+    pipe2.wait()
+    pipe2.wait()
+
+
 def test_multi_tuner_pipeline_argument_checks(gpu):
     import ctypes as C
     from sdrtrunk_b200.dsp import Bank, ComplexPolyphaseChannelizerM2, Pipeline

@@ -42,6 +42,13 @@ def main():
             per = max(ms, wall) / 5
             print("host chunks %2d: e2e %.3f ms/step (events %.3f, wall %.3f) = %.2f GS/s" %
                   (chunks, per, ms / 5, wall / 5, w.total_complex / (per * 1e-3) / 1e9), flush=True)
+    for chunks in [int(a) for a in sys.argv[2:]] or [4, 8]:
+        w.pipeline.setChunks(chunks)
+        ms, wall = timed(w.step_host_stream, w.stream, 6, 3)
+        w.stream_drain()
+        per = max(ms, wall) / 6
+        print("host chunks %2d, two calls in flight (submit / wait): e2e %.3f ms/step (events %.3f, wall %.3f) = %.2f GS/s" %
+              (chunks, per, ms / 6, wall / 6, w.total_complex / (per * 1e-3) / 1e9), flush=True)
     w.pipeline.setChunks(8)
     w.set_format("f32")
     ms, _ = timed(w.step_device, w.stream, 5, 3)
