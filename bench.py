@@ -710,13 +710,15 @@ def measure_tuner(w, args, world, timed, full=True):
         if w.pipeline is not None:
             # the chain's host-buffer path takes what a 20 MS/s USB tuner delivers: signed 8-bit I/Q (HackRF;
             # SignedByteSampleConverter), converted on the device in front of the channelizer
-            blocking = e2e_leg("s8", "tuner-native signed 8-bit I/Q in pinned host buffers (SignedByteSampleConverter "
-                                     "format, converted on the device), dibits + counts back to pinned host buffers; one "
-                                     "blocking sdrgpu_pipeline_process_multi call per step")
-            res["e2e"] = e2e_stream_leg("s8", "tuner-native signed 8-bit I/Q in pinned host buffers (SignedByteSampleConverter "
-                                              "format, converted on the device), dibits + counts back to pinned host buffers; "
-                                              "a continuous stream: sdrgpu_pipeline_submit_multi / _wait with two steps in "
-                                              "flight, every step's H2D and D2H copies inside the timed region")
+            note = ("tuner-native signed 8-bit I/Q in pinned host buffers (SignedByteSampleConverter format, converted on the "
+                    "device), dibits + counts back to pinned host buffers; ")
+            blocking = e2e_leg("s8", note + "one blocking sdrgpu_pipeline_process_multi call per step")
+            stream = e2e_stream_leg("s8", note + "a continuous stream: sdrgpu_pipeline_submit_multi / _wait with two steps in "
+                                                 "flight, every step's H2D and D2H copies inside the timed region")
+            # the host side picks the call that suits its bank: the stream wins once the bank fills the GPU, a single tuner's
+            # latency-bound step is served better by the chunked blocking call
+            res["e2e"] = dict(stream if stream["value"] >= blocking["value"] else blocking)
+            res["e2e"]["stream_two_in_flight"] = {"value": stream["value"], "unit": UNIT, "ms_per_step": stream["ms_per_step"]}
             res["e2e"]["blocking_call"] = {"value": blocking["value"], "unit": UNIT, "ms_per_step": blocking["ms_per_step"]}
             if full and w.T == 1:
                 res["e2e_f32_input"] = e2e_leg("f32", "float32 I/Q in pinned host buffers (the reference's float[] buffers)")

@@ -10,7 +10,7 @@
  *  - all sample data is IEEE float32, complex data interleaved I,Q (the reference's float[] buffers).
  *  - `mem` arguments say where a caller pointer lives: SDRGPU_HOST (pageable or pinned host memory) or
  *    SDRGPU_DEVICE (device memory of the handle's GPU).  The library never keeps a caller pointer after
- *    the call returns; host outputs are complete on return, device outputs are stream-ordered on the
+ *    the call returns (one exception, by name: sdrgpu_pipeline_submit_multi); host outputs are complete on return, device outputs are stream-ordered on the
  *    handle's stream (sdrgpu_*_sync or the caller's own stream sync).
  *  - a handle is bound to the device that was current in sdrgpu_init, owns its device state (filter
  *    history, PLL, timing) and is NOT thread safe: one host thread <-> one handle <-> one CUDA stream.

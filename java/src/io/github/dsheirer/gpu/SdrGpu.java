@@ -93,6 +93,11 @@ public final class SdrGpu
     static final MethodHandle PIPELINE_DESTROY = h("sdrgpu_pipeline_destroy", FunctionDescriptor.of(JAVA_INT, ADDRESS));
     static final MethodHandle PIPELINE_PROCESS_MULTI = h("sdrgpu_pipeline_process_multi",
         FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, JAVA_INT, ADDRESS, JAVA_INT, ADDRESS, JAVA_LONG, ADDRESS, JAVA_INT));
+    /** asynchronous form for a continuous stream: (pipeline, iq[], nFloats, symbols, symbolStride, counts); at most two in flight */
+    static final MethodHandle PIPELINE_SUBMIT_MULTI = h("sdrgpu_pipeline_submit_multi",
+        FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, ADDRESS, JAVA_INT, ADDRESS));
+    /** returns when the OLDEST submitted call has its dibits and counts in the host buffers it was given */
+    static final MethodHandle PIPELINE_WAIT = h("sdrgpu_pipeline_wait", FunctionDescriptor.of(JAVA_INT, ADDRESS));
     static final MethodHandle DESIGN_REMEZ_LOW_PASS = h("sdrgpu_design_remez_low_pass",
         FunctionDescriptor.of(JAVA_INT, JAVA_DOUBLE, JAVA_DOUBLE, JAVA_DOUBLE, JAVA_DOUBLE, JAVA_DOUBLE, JAVA_INT, JAVA_INT, JAVA_INT,
             ADDRESS, JAVA_INT, ADDRESS));
