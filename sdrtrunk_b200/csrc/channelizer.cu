@@ -386,7 +386,11 @@ __device__ __forceinline__ void fb_thread(const ChanParams &p, const float2 *__r
 }
 
 template <int M, int R1, int R2, int NB, int TT, int NT, int MINB, bool RAW>
-__global__ void __launch_bounds__(NT, MINB) pfb2_kernel(const ChanParams p)
+// M = 800: bounded as if the CTA had one more warp -- ptxas then settles for 96 registers instead of the 128 the bound allows,
+// without a spill and at the same speed (1.40 ms per 8 launches either way), which leaves a quarter of the register file to
+// whatever runs beside the channelizers (the oscillator producers of frequency-corrected channels: their one-warp CTAs
+// otherwise wait for -- or keep out -- a whole 32 K-register channelizer CTA).  M = 400 needs its 72 (64: a spill, 1 % slower).
+__global__ void __launch_bounds__(M == 800 ? NT + 32 : NT, MINB) pfb2_kernel(const ChanParams p)
 {
     using L = Pfb2Layout<M, R1, R2, NB, TT, NT>;
     constexpr int half = M / 2, SV = L::SV, XS = L::XS, R2P = L::R2P, YB = L::YB;
@@ -864,6 +868,7 @@ struct sdrgpu_channelizer {
     cudaStream_t osc_stream = nullptr;
     cudaEvent_t ev_mix = nullptr, ev_osc = nullptr;
     bool osc_pending = false;
+    bool mix_recorded = false;   // ev_mix marks the end of the last kernel that read the rings
     SynthFilter synth{};
     int gain_exact = 1;
     int identity = 0;
@@ -969,7 +974,8 @@ sdrgpu_status upload_selection(sdrgpu_channelizer *h)
             SDRGPU_CUDA(cudaEventCreateWithFlags(&h->ev_mix, cudaEventDisableTiming));
             SDRGPU_CUDA(cudaEventCreateWithFlags(&h->ev_osc, cudaEventDisableTiming));
         }
-        h->osc_ring_len = (h->max_blocks + 8 + 1) & ~1;   // even: the producer stores pairs
+        // two calls' worth: a pipeline tops the ring up at the START of a call, for the call after it (chan_osc_ahead)
+        h->osc_ring_len = (2 * h->max_blocks + 8 + 1) & ~1;   // even: the producer stores pairs
         std::vector<float2> start(mix.size(), make_float2(0.0f, -1.0f));   // Oscillator.java:24
         SDRGPU_CUDA(cudaMalloc(&h->d_mix, sizeof(MixChannel) * mix.size()));
         SDRGPU_CUDA(cudaMalloc(&h->d_mix_state, sizeof(float2) * mix.size()));
@@ -1169,11 +1175,12 @@ sdrgpu_status sdrgpu::chan_enqueue(sdrgpu_channelizer *h, const float2 *d_in, in
                 count_launch();
             }
             h->osc_consumed += n_blocks;
+            SDRGPU_CUDA(cudaEventRecord(h->ev_mix, h->stream));
+            h->mix_recorded = true;
             // top the ring up to a call's worth on the side stream, behind the kernel that has just read it
             const int pgrid = (h->n_mix + 31) / 32;
             const int top_up = h->max_blocks - (int)(h->osc_produced - h->osc_consumed);
             if (top_up > 0) {
-                SDRGPU_CUDA(cudaEventRecord(h->ev_mix, h->stream));
                 SDRGPU_CUDA(cudaStreamWaitEvent(h->osc_stream, h->ev_mix, 0));
                 // Round 1 kept other blocks off the producer's SMs by asking for 220 KB of shared memory it never touched
                 // (SDRGPU_OSC_EXCLUSIVE=1 still does); that only worked for one pipeline per GPU and starves everything else
@@ -1261,6 +1268,35 @@ const float2 *sdrgpu::chan_convert(sdrgpu_channelizer *h, const void *iq_device,
     }
     return h->d_in + first;
 }
+// Oscillator look-ahead of a pipeline: at the START of a call (before its channelizer kernels) the rings are topped up to
+// two calls' worth, i.e. the values of the NEXT call are produced beside this call's channelizer / first FIR launches --
+// throughput-bound kernels that lose little to 200 latency-bound warps -- instead of behind them, beside the demodulator,
+// whose launch time is set by its most loaded scheduler (8 tuners, all 6400 channels corrected: 9.1 -> see DESIGN.md).
+sdrgpu_status sdrgpu::chan_osc_ahead(sdrgpu_channelizer *h)
+{
+    static const int ahead_env = getenv("SDRGPU_OSC_AHEAD") ? atoi(getenv("SDRGPU_OSC_AHEAD")) : 1;
+    if (!ahead_env || h->n_mix <= 0 || !h->d_osc) return SDRGPU_OK;
+    const int top_up = 2 * h->max_blocks - (int)(h->osc_produced - h->osc_consumed);
+    if (top_up <= 0) return SDRGPU_OK;
+    // the producer in flight (this call's values) first: ev_osc is about to be re-recorded
+    if (h->osc_pending) {
+        SDRGPU_CUDA(cudaStreamWaitEvent(h->stream, h->ev_osc, 0));
+        h->osc_pending = false;
+        h->osc_safe = h->osc_produced;
+    }
+    if (h->mix_recorded) SDRGPU_CUDA(cudaStreamWaitEvent(h->osc_stream, h->ev_mix, 0));   // the slots' last reader
+    osc_produce_kernel<<<(h->n_mix + 31) / 32, 32, 0, h->osc_stream>>>(h->d_mix, h->d_mix_state, h->d_osc, h->osc_ring_len,
+                                                                       h->osc_produced, top_up, h->n_mix);
+    SDRGPU_CUDA(cudaGetLastError());
+    SDRGPU_CUDA(cudaEventRecord(h->ev_osc, h->osc_stream));
+    h->osc_produced += top_up;
+    h->osc_pending = true;
+    count_launch();
+    return SDRGPU_OK;
+}
+
+cudaStream_t sdrgpu::chan_osc_stream(const sdrgpu_channelizer *h) { return h->n_mix > 0 ? h->osc_stream : nullptr; }
+
 void sdrgpu::chan_swap_staging(sdrgpu_channelizer *h)
 {
     std::swap(h->d_in, h->d_in_alt);

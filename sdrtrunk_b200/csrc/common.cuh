@@ -67,6 +67,8 @@ size_t chan_complex_bytes(const sdrgpu_channelizer *h);   // bytes of one comple
 int chan_half(const sdrgpu_channelizer *h);
 void chan_swap_staging(sdrgpu_channelizer *h);   // host-input staging buffers alternate between the calls of an asynchronous pipeline
 const void *chan_staging(const sdrgpu_channelizer *h);
+cudaStream_t chan_osc_stream(const sdrgpu_channelizer *h);   // nullptr without frequency-corrected channels (call traces)
+sdrgpu_status chan_osc_ahead(sdrgpu_channelizer *h);   // frequency-corrected channels: produce the next call's oscillator values now
 void chan_set_throttled(sdrgpu_channelizer *h, bool on);   // next launches share the GPU with the demodulator (SDRGPU_TUNE_PFB_CTAS_PER_SM)
 int chan_max_in(const sdrgpu_channelizer *h);
 int chan_leftover(const sdrgpu_channelizer *h);  // samples buffered that did not fill a block yet (mSampleBufferPointer)   // complex samples one process call may carry (max_input_floats / 2)
