@@ -1011,6 +1011,68 @@ def test_asynchronous_pipeline_calls_equal_the_synchronous_sequence(gpu, fmt):
     pipe2.wait()
 
 
+def test_frequency_corrected_channels_through_the_filters_first_and_asynchronous_schedules(gpu):
+    """Frequency-corrected channels in a two-tuner pipeline: the filters-first schedule (device-resident input, and the
+    asynchronous stream built on it) launches the oscillator producers at the START of a call, two calls ahead
+    (chan_osc_ahead, two-call rings), where the single-pass call tops its ring up behind the channelizer.  Every row's
+    dibits must be the same through all three, over calls of different lengths that wrap the rings."""
+    import ctypes as C
+    from sdrtrunk_b200.dsp import Bank, ComplexPolyphaseChannelizerM2, Pipeline
+    m, n_ch = 96, 30 * 1024
+    rng = np.random.default_rng(97)
+    bins = [[2, 30, 77], [5, 6, 95]]
+    offsets = [[37, -53, 120], [-200, 9, 64]]
+    xs = [_tuner_stream(rng, m, n_ch, b) for b in bins]
+    taps, fir = oracle.sinc_m2_channelizer(25000.0, m, 9), c4fm_taps()
+    rows = sum(len(b) for b in bins)
+    unit = m * 1024
+    sizes = [6 * unit, 8 * unit, 3 * unit, 8 * unit]
+    sizes.append(xs[0].size - sum(sizes))
+    edges = np.cumsum([0] + sizes)
+
+    def pipeline(device_chunks):
+        chans = []
+        for k in range(2):
+            ch = ComplexPolyphaseChannelizerM2(taps, 2400000, m, maxInputFloats=8 * unit)
+            ch.setOutputChannels([([b], off) for b, off in zip(bins[k], offsets[k])])
+            chans.append(ch)
+        pipe = Pipeline(chans, Bank.preset(gpu.PRESET_P25_C4FM, rows, 50000.0, fir, max_samples_per_call=9 * 1024))
+        pipe.setChunks(1)
+        pipe.setDeviceChunks(device_chunks)
+        return pipe
+
+    single = pipeline(1)
+    want = [single.process([x[a:b] for x in xs]) for a, b in zip(edges[:-1], edges[1:])]
+    assert sum(w.size for w in want[1]) > 1000
+
+    first = pipeline(2)          # device-resident input, two time chunks: the filters-first schedule
+    L = gpu.lib()
+    for i, (a, b) in enumerate(zip(edges[:-1], edges[1:])):
+        ptrs = []
+        for x in xs:
+            seg = np.ascontiguousarray(x[a:b])
+            d = C.c_void_p()
+            gpu.check(L.sdrgpu_device_alloc(C.byref(d), max(seg.nbytes, 16)))
+            gpu.check(L.sdrgpu_memcpy(d, gpu.ptr(seg), seg.nbytes, gpu.DEVICE, gpu.HOST))
+            ptrs.append(d)
+        got = first.process([d.value for d in ptrs], gpu.DEVICE, int(b - a))
+        for d in ptrs:
+            L.sdrgpu_device_free(d)
+        for r in range(rows):
+            assert np.array_equal(got[r], want[i][r]), ("filters-first", i, r)
+
+    stream = pipeline(2)
+    got = []
+    for i, (a, b) in enumerate(zip(edges[:-1], edges[1:])):
+        stream.submit([x[a:b].copy() for x in xs])
+        if i >= 1:
+            got.append(stream.wait())
+    got.append(stream.wait())
+    for i in range(len(want)):
+        for r in range(rows):
+            assert np.array_equal(got[i][r], want[i][r]), ("stream", i, r)
+
+
 def test_multi_tuner_pipeline_argument_checks(gpu):
     import ctypes as C
     from sdrtrunk_b200.dsp import Bank, ComplexPolyphaseChannelizerM2, Pipeline
