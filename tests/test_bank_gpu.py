@@ -1011,6 +1011,58 @@ def test_asynchronous_pipeline_calls_equal_the_synchronous_sequence(gpu, fmt):
     pipe2.wait()
 
 
+def test_asynchronous_pipeline_random_call_sizes(gpu):
+    """a longer stream through submit / wait with random call sizes (whole buffers, ragged, shorter than a chunk, empty),
+    waits taken late or early (one or two calls in flight), 8-bit tuner samples: every call's dibits equal the synchronous
+    sequence's -- the ordering of the two calls' copies, kernels and staging is by events only"""
+    from sdrtrunk_b200.dsp import Bank, ComplexPolyphaseChannelizerM2, Pipeline
+    m, n_ch = 96, 96 * 1024
+    rng = np.random.default_rng(131)
+    bins = [[1, 40], [9, 90]]
+    xs = [np.clip(np.round(_tuner_stream(rng, m, n_ch, b) * 128.0 * 4), -128, 127).astype(np.int8) for b in bins]
+    taps, fir = oracle.sinc_m2_channelizer(25000.0, m, 9), c4fm_taps()
+    rows = 4
+    unit = m * 1024
+    sizes, left = [], xs[0].size
+    while left > 0:
+        kind = rng.integers(0, 5)
+        n = [int(rng.integers(2, 9)) * unit, int(rng.integers(1, 8 * unit // 2)) * 2, unit // 2, 0, 8 * unit][kind]
+        n = min(n, left)
+        sizes.append(n)
+        left -= n
+    edges = np.cumsum([0] + sizes)
+
+    def pipeline():
+        chans = []
+        for k in range(2):
+            ch = ComplexPolyphaseChannelizerM2(taps, 2400000, m, maxInputFloats=8 * unit)
+            ch.setChannels(bins[k])
+            ch.setSampleFormat("s8")
+            chans.append(ch)
+        pipe = Pipeline(chans, Bank.preset(gpu.PRESET_P25_C4FM, rows, 50000.0, fir, max_samples_per_call=9 * 1024))
+        pipe.setChunks(3)
+        pipe.setDeviceChunks(2)
+        return pipe
+
+    sync = pipeline()
+    want = [sync.process([x[a:b] for x in xs]) for a, b in zip(edges[:-1], edges[1:])]
+    pipe = pipeline()
+    got, in_flight = [], 0
+    for a, b in zip(edges[:-1], edges[1:]):
+        if in_flight == 2 or (in_flight == 1 and rng.integers(0, 2)):
+            got.append(pipe.wait())
+            in_flight -= 1
+        pipe.submit([x[a:b].copy() for x in xs])
+        in_flight += 1
+    while in_flight:
+        got.append(pipe.wait())
+        in_flight -= 1
+    assert len(got) == len(want) and len(want) > 12
+    for i in range(len(want)):
+        for r in range(rows):
+            assert np.array_equal(got[i][r], want[i][r]), (i, r, sizes[i])
+
+
 def test_frequency_corrected_channels_through_the_filters_first_and_asynchronous_schedules(gpu):
     """Frequency-corrected channels in a two-tuner pipeline: the filters-first schedule (device-resident input, and the
     asynchronous stream built on it) launches the oscillator producers at the START of a call, two calls ahead
