@@ -526,7 +526,7 @@ class TunerWorkload:
             self.bank.setStream(self.stream.cuda_stream)
             self.pipeline = Pipeline(self.chans, self.bank)
             self.chunks = int(os.environ.get("SDRGPU_BENCH_CHUNKS", "8"))
-            self.device_chunks = int(os.environ.get("SDRGPU_BENCH_DEVICE_CHUNKS", "1" if tuners == 1 else "4"))
+            self.device_chunks = int(os.environ.get("SDRGPU_BENCH_DEVICE_CHUNKS", "1" if tuners == 1 else "6"))
             self.pipeline.setChunks(self.chunks)
             self.pipeline.setDeviceChunks(self.device_chunks)
             self.sym_stride = self.n_blocks // 8 + 64          # > 4800/50000 symbols per sample

@@ -374,8 +374,9 @@ sdrgpu_status sdrgpu_pipeline_process_multi(sdrgpu_pipeline *p, const void *cons
 sdrgpu_status sdrgpu_pipeline_submit_multi(sdrgpu_pipeline *p, const void *const *iq, int n_floats, uint8_t *symbols,
                                            int symbol_stride, int *counts);
 sdrgpu_status sdrgpu_pipeline_wait(sdrgpu_pipeline *p);
-/* time chunks for device-resident input (default 1: nothing to copy, but with many channels the latency-bound
- * demodulator of chunk i overlaps the issue-bound channelizer / FIR kernels of chunk i+1) */
+/* time chunks for device-resident input, and for the asynchronous calls above (nothing to copy, but with many channels the
+ * latency-bound demodulator of chunk i overlaps the FIR kernels of chunk i+1; the first chunks are a quarter and half a
+ * chunk).  Default: by bank size -- 6 from 2400 channels (several tuners in one bank), else 1 */
 sdrgpu_status sdrgpu_pipeline_set_device_chunks(sdrgpu_pipeline *p, int chunks);
 
 #ifdef __cplusplus
