@@ -80,3 +80,18 @@ def test_header_is_plain_c():
         pytest.skip("no C compiler")
     subprocess.check_call([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", header])
     subprocess.check_call([gcc, "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", "-x", "c++", header])
+
+
+def test_null_handles_are_refused_not_dereferenced():
+    """argument checks run before anything touches the device: every pipeline entry point answers INVALID_ARG to a NULL
+    handle (the Java shim maps it to IllegalArgumentException), also without a GPU"""
+    from sdrtrunk_b200 import native
+    L = native.lib()
+    invalid = 1   # SDRGPU_ERR_INVALID_ARG
+    assert L.sdrgpu_pipeline_wait(None) == invalid
+    assert L.sdrgpu_pipeline_submit_multi(None, None, 0, None, 0, None) == invalid
+    assert L.sdrgpu_pipeline_process_multi(None, None, 0, native.HOST, None, 0, None, 0, None, native.HOST) == invalid
+    assert L.sdrgpu_pipeline_set_chunks(None, 4) == invalid
+    assert L.sdrgpu_pipeline_set_device_chunks(None, 4) == invalid
+    assert L.sdrgpu_pipeline_wait(None) == invalid
+    assert b"NULL" in L.sdrgpu_last_error()
