@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _latest(pattern):
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", pattern)), key=os.path.getmtime)
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", pattern)))   # round tags sort by name: r19 < r2j < r3a < r4a < r5e
     if not files:
         pytest.skip("no committed bench output")
     lines = [l for l in open(files[-1]).read().splitlines() if l.startswith("{")]
