@@ -17,6 +17,9 @@ head -c 600 $out/${tag}_bench_reference.json; echo
 # (compute-sanitizer memcheck / racecheck of the smoke path were part of this round until the pool closed the tool:
 #  "compute-sanitizer is closed on this pool and stays closed: runs under it have left GPUs needing a reset" -- r2j_memcheck.log.
 #  Bounds are covered by the parity tests instead: ragged / oversized / empty calls, odd channel counts, partial tiles.)
+# side measurements behind DESIGN.md section 4 / 5 (seconds each): FIR stage alone, blocking against streamed e2e step
+python tools/fir_time.py 6400 > $out/${tag}_fir_time.txt 2>&1
+python tools/e2e_probe.py 8 8 > $out/${tag}_e2e_probe.txt 2>&1
 if [ "$2" != "noncu" ]; then
 CMD="python bench.py --steps 2 --warmup 3 --no-extra --no-cpu-baseline --device-only"
 $CMD > $out/${tag}_plain.log 2>&1 &&
